@@ -1,0 +1,80 @@
+// common.cuh -- error plumbing and small device helpers shared by the translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/pds_b200.h"
+
+namespace pds {
+
+// thread-local message behind pds_last_error()
+void set_error(const char* fmt, ...);
+
+#define PDS_CUDA_CHECK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t err__ = (expr);                                                           \
+    if (err__ != cudaSuccess) {                                                           \
+      ::pds::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,               \
+                       cudaGetErrorString(err__));                                        \
+      return PDS_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define PDS_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      ::pds::set_error(__VA_ARGS__);  \
+      return PDS_ERR_INVALID;         \
+    }                                 \
+  } while (0)
+
+// Number of SMs of the current device (cached per device).
+int sm_count(int device);
+
+#ifdef __CUDACC__
+
+// ---- Philox4x32-10 counter-based generator: the dither stream -----------------------------
+// One standard normal per (seed, utterance, sample) triple, independent of how utterances are
+// batched, tiled or sharded over GPUs (reference only pins mean/std).
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t utt, uint64_t sample) {
+  uint32_t c0 = (uint32_t)sample, c1 = (uint32_t)(sample >> 32), c2 = utt, c3 = 0x5eed5eedu;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int round = 0; round < 10; ++round) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  // Box-Muller on two 32-bit uniforms in (0, 1)
+  const float u1 = ((float)c0 + 0.5f) * 2.3283064365386963e-10f;
+  const float u2 = ((float)c1 + 0.5f) * 2.3283064365386963e-10f;
+  const float radius = sqrtf(-2.0f * __logf(fmaxf(u1, 1e-12f)));
+  return radius * __cosf(6.283185307179586f * u2);
+}
+
+template <typename T>
+__device__ __forceinline__ float load_sample(const T* p, long long i) {
+  return (float)p[i];
+}
+
+// symmetric ("half-sample") reflection of an out-of-range index, numpy.pad(..., 'symmetric')
+__device__ __forceinline__ long long reflect_index(long long g, long long len) {
+  if (g >= 0 && g < len) return g;
+  const long long period = 2 * len;
+  long long m = g % period;
+  if (m < 0) m += period;
+  return m < len ? m : period - 1 - m;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace pds

@@ -1,0 +1,299 @@
+// post.cu -- pre/post-processor kernels: Deltas (K4), CMVN statistics (K5) and application (K6),
+// plus stand-alone pre-emphasis / dither passes for pipelines that cannot fuse them.
+//
+// All three post kernels are HBM-bound streaming passes over the packed (rows x cols) float32
+// feature matrix; they are written for coalesced row-major access and enough resident CTAs to
+// cover HBM latency (grid sized from the SM count), not for arithmetic throughput.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pds {
+
+// ------------------------------------------------------------------------------------------
+// Deltas: out[r, k*cols + c] = sum_j f_k[j] * in[clamp(r + j - half_k, utt_lo, utt_hi - 1), c]
+// (post.py:462-491 with pad_mode='edge', concatenate=True, axis=0, target_axis=-1)
+// ------------------------------------------------------------------------------------------
+constexpr int kDeltaMaxTaps = 240;
+constexpr int kDeltaMaxOrders = 8;
+constexpr int kDeltaRows = 32;  // rows of output per CTA
+
+struct DeltaParams {
+  const float* in;
+  float* out;
+  const long long* row_off;
+  long long total_rows;
+  long long n_utts;
+  int cols;
+  int orders;
+  int half_max;
+  int filt_off[kDeltaMaxOrders];
+  int filt_len[kDeltaMaxOrders];
+  float taps[kDeltaMaxTaps];
+};
+
+__global__ void __launch_bounds__(256) deltas_kernel(const __grid_constant__ DeltaParams p) {
+  extern __shared__ __align__(16) float s_rows[];  // (kDeltaRows + 2*half_max) x cols
+  __shared__ long long s_utt_of_first;
+  const int tid = threadIdx.x;
+  const long long r0 = (long long)blockIdx.x * kDeltaRows;
+  const int nrows = (int)min((long long)kDeltaRows, p.total_rows - r0);
+  if (tid == 0) {
+    // utterance containing r0: largest u with row_off[u] <= r0 (skipping empty utterances later)
+    long long lo = 0, hi = p.n_utts;
+    while (hi - lo > 1) {
+      const long long mid = (lo + hi) >> 1;
+      if (p.row_off[mid] <= r0) lo = mid; else hi = mid;
+    }
+    s_utt_of_first = lo;
+  }
+  __syncthreads();
+  const int H = p.half_max, cols = p.cols;
+  const int stage_rows = nrows + 2 * H;
+  // stage rows r0-H .. r0+nrows+H (clamped to the matrix); per-utterance clamping happens on use
+  for (int i = tid; i < stage_rows * cols; i += blockDim.x) {
+    const int sr = i / cols, c = i - sr * cols;
+    long long r = r0 - H + sr;
+    r = max(0LL, min(p.total_rows - 1, r));
+    s_rows[i] = p.in[r * cols + c];
+  }
+  __syncthreads();
+  const int out_cols = cols * (p.orders + 1);
+  for (int i = tid; i < nrows * cols; i += blockDim.x) {
+    const int lr = i / cols, c = i - lr * cols;
+    const long long r = r0 + lr;
+    long long u = s_utt_of_first;
+    while (u + 1 < p.n_utts && p.row_off[u + 1] <= r) ++u;  // few steps: tiles rarely span utterances
+    const long long u_lo = p.row_off[u], u_hi = p.row_off[u + 1];
+    float* __restrict__ dst = p.out + r * out_cols + c;
+    dst[0] = s_rows[(lr + H) * cols + c];
+    for (int k = 0; k < p.orders; ++k) {
+      const int len = p.filt_len[k], half = (len - 1) / 2;
+      const float* f = p.taps + p.filt_off[k];
+      float acc = 0.f;
+      for (int j = 0; j < len; ++j) {
+        long long rr = r + j - half;
+        rr = max(u_lo, min(u_hi - 1, rr));
+        acc = fmaf(f[j], s_rows[((int)(rr - r0) + H) * cols + c], acc);
+      }
+      dst[(k + 1) * cols] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// CMVN statistics: per-column sum and sum of squares in float64 (post.py:175-191)
+// ------------------------------------------------------------------------------------------
+constexpr int kStatsThreadsX = 32;
+constexpr int kStatsThreadsY = 8;
+
+__global__ void __launch_bounds__(kStatsThreadsX* kStatsThreadsY)
+    cmvn_stats_kernel(const float* __restrict__ feats, long long n_rows, int cols,
+                      double* __restrict__ stats) {
+  // blockIdx.y picks a 32-column stripe, blockIdx.x a slab of rows; thread.x = column (coalesced),
+  // thread.y strides rows.
+  __shared__ double s_sum[kStatsThreadsY][kStatsThreadsX];
+  __shared__ double s_sq[kStatsThreadsY][kStatsThreadsX];
+  const int c = blockIdx.y * kStatsThreadsX + threadIdx.x;
+  double sum = 0.0, sq = 0.0;
+  if (c < cols) {
+    const long long stride = (long long)gridDim.x * kStatsThreadsY;
+    long long r = (long long)blockIdx.x * kStatsThreadsY + threadIdx.y;
+    // four independent loads in flight per thread
+    for (; r + 3 * stride < n_rows; r += 4 * stride) {
+      const float a = feats[r * cols + c], b = feats[(r + stride) * cols + c];
+      const float d = feats[(r + 2 * stride) * cols + c], e = feats[(r + 3 * stride) * cols + c];
+      sum += (double)a + (double)b + (double)d + (double)e;
+      sq += (double)a * a + (double)b * b + (double)d * d + (double)e * e;
+    }
+    for (; r < n_rows; r += stride) {
+      const float a = feats[r * cols + c];
+      sum += (double)a;
+      sq += (double)a * a;
+    }
+  }
+  s_sum[threadIdx.y][threadIdx.x] = sum;
+  s_sq[threadIdx.y][threadIdx.x] = sq;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+#pragma unroll
+    for (int y = 1; y < kStatsThreadsY; ++y) {
+      sum += s_sum[y][threadIdx.x];
+      sq += s_sq[y][threadIdx.x];
+    }
+    atomicAdd(stats + c, sum);
+    atomicAdd(stats + (cols + 1) + c, sq);
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0)
+    atomicAdd(stats + cols, (double)n_rows);
+}
+
+// ------------------------------------------------------------------------------------------
+// CMVN apply: y = x * scale[c] - mean[c] * scale[c]  (post.py:264-294)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    cmvn_apply_kernel(const float* __restrict__ feats, float* __restrict__ out, long long n_rows,
+                      int cols, const double* __restrict__ stats, int norm_var,
+                      int* __restrict__ zero_var) {
+  extern __shared__ __align__(16) float s_tab[];  // scale[cols] | shift[cols]
+  float* s_scale = s_tab;
+  float* s_shift = s_tab + cols;
+  const double count = stats[cols];
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const double mean = stats[c] / count;
+    double scale = 1.0;
+    if (norm_var) {
+      double var = stats[cols + 1 + c] / count - mean * mean;
+      if (fabs(var) <= 1e-8) {  // np.isclose(var, 0)
+        var = 1.0;
+        if (zero_var) *zero_var = 1;
+      }
+      scale = 1.0 / sqrt(var);
+    }
+    s_scale[c] = (float)scale;
+    s_shift[c] = (float)(mean * scale);
+  }
+  __syncthreads();
+  const long long total = n_rows * cols;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int c = (int)(i % cols);
+  const int step = (int)(stride % cols);
+  for (; i < total; i += stride) {
+    out[i] = fmaf(feats[i], s_scale[c], -s_shift[c]);
+    c += step;
+    if (c >= cols) c -= cols;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone pre-processors over a packed batch; blockIdx.y = utterance
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    preemph_kernel(const float* __restrict__ in, float* __restrict__ out,
+                   const long long* __restrict__ sig_off, const long long* __restrict__ sig_len,
+                   float coeff) {
+  const long long off = sig_off[blockIdx.y], len = sig_len[blockIdx.y];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    const float x = in[off + i];
+    out[off + i] = i > 0 ? fmaf(-coeff, in[off + i - 1], x) : x;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    dither_kernel(const float* __restrict__ in, float* __restrict__ out,
+                  const long long* __restrict__ sig_off, const long long* __restrict__ sig_len,
+                  float coeff, unsigned long long seed) {
+  const long long off = sig_off[blockIdx.y], len = sig_len[blockIdx.y];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride)
+    out[off + i] = in[off + i] + coeff * philox_normal(seed, blockIdx.y, (unsigned long long)i);
+}
+
+}  // namespace pds
+
+using namespace pds;
+
+extern "C" int pds_deltas(const float* d_in, float* d_out, int64_t total_rows, int32_t n_cols,
+                          int64_t n_utts, const int64_t* d_row_off, int32_t orders,
+                          const float* h_filters, const int32_t* h_filter_len, void* stream) {
+  PDS_REQUIRE(total_rows >= 0 && n_cols >= 1 && n_utts >= 0 && orders >= 0, "bad shape");
+  if (total_rows == 0) return PDS_OK;
+  PDS_REQUIRE(d_in && d_out && d_row_off && n_utts >= 1, "null buffer");
+  PDS_REQUIRE(orders <= kDeltaMaxOrders, "at most %d delta orders are supported", kDeltaMaxOrders);
+  PDS_REQUIRE(orders == 0 || (h_filters && h_filter_len), "null filter table");
+  DeltaParams p;
+  p.in = d_in, p.out = d_out, p.row_off = reinterpret_cast<const long long*>(d_row_off);
+  p.total_rows = total_rows, p.n_utts = n_utts, p.cols = n_cols, p.orders = orders, p.half_max = 0;
+  int at = 0;
+  for (int k = 0; k < orders; ++k) {
+    const int len = h_filter_len[k];
+    PDS_REQUIRE(len >= 1 && (len % 2) == 1, "delta filter %d has even/empty length %d", k, len);
+    if (at + len > kDeltaMaxTaps) {
+      set_error("delta filters need %d taps (max %d)", at + len, kDeltaMaxTaps);
+      return PDS_ERR_UNSUPPORTED;
+    }
+    p.filt_off[k] = at, p.filt_len[k] = len;
+    for (int j = 0; j < len; ++j) p.taps[at + j] = h_filters[at + j];
+    at += len;
+    p.half_max = std::max(p.half_max, (len - 1) / 2);
+  }
+  const size_t smem = sizeof(float) * (size_t)(kDeltaRows + 2 * p.half_max) * n_cols;
+  if (smem > 200 * 1024) {
+    set_error("deltas: %d columns x %d context rows exceed shared memory", n_cols, p.half_max);
+    return PDS_ERR_UNSUPPORTED;
+  }
+  if (smem > 48 * 1024)
+    PDS_CUDA_CHECK(cudaFuncSetAttribute(deltas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long grid = (total_rows + kDeltaRows - 1) / kDeltaRows;
+  deltas_kernel<<<(unsigned)grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  PDS_CUDA_CHECK(cudaGetLastError());
+  return PDS_OK;
+}
+
+extern "C" int pds_cmvn_accumulate(const float* d_feats, int64_t n_rows, int32_t n_cols,
+                                   double* d_stats, void* stream) {
+  PDS_REQUIRE(n_rows >= 0 && n_cols >= 1, "bad shape");
+  if (n_rows == 0) return PDS_OK;
+  PDS_REQUIRE(d_feats && d_stats, "null buffer");
+  int device = 0;
+  PDS_CUDA_CHECK(cudaGetDevice(&device));
+  const int stripes = (n_cols + kStatsThreadsX - 1) / kStatsThreadsX;
+  // ~8 resident CTAs per SM in total, but never more slabs than there are row groups
+  long long slabs = std::max(1, sm_count(device) * 8 / stripes);
+  slabs = std::min<long long>(slabs, (n_rows + kStatsThreadsY - 1) / kStatsThreadsY);
+  dim3 grid((unsigned)slabs, (unsigned)stripes), block(kStatsThreadsX, kStatsThreadsY);
+  cmvn_stats_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(d_feats, n_rows, n_cols, d_stats);
+  PDS_CUDA_CHECK(cudaGetLastError());
+  return PDS_OK;
+}
+
+extern "C" int pds_cmvn_apply(const float* d_feats, float* d_out, int64_t n_rows, int32_t n_cols,
+                              const double* d_stats, int32_t norm_var, int32_t* d_zero_var,
+                              void* stream) {
+  PDS_REQUIRE(n_rows >= 0 && n_cols >= 1, "bad shape");
+  if (n_rows == 0) return PDS_OK;
+  PDS_REQUIRE(d_feats && d_out && d_stats, "null buffer");
+  int device = 0;
+  PDS_CUDA_CHECK(cudaGetDevice(&device));
+  const long long total = n_rows * (long long)n_cols;
+  long long grid = std::min<long long>((total + 255) / 256, (long long)sm_count(device) * 8);
+  cmvn_apply_kernel<<<(unsigned)grid, 256, 2 * sizeof(float) * n_cols, static_cast<cudaStream_t>(stream)>>>(
+      d_feats, d_out, n_rows, n_cols, d_stats, norm_var, d_zero_var);
+  PDS_CUDA_CHECK(cudaGetLastError());
+  return PDS_OK;
+}
+
+extern "C" int pds_preemphasize(const float* d_in, float* d_out, int64_t n_utts,
+                                const int64_t* d_sig_off, const int64_t* d_sig_len,
+                                int64_t total_samples, float coeff, void* stream) {
+  PDS_REQUIRE(n_utts >= 0 && total_samples >= 0, "bad shape");
+  if (n_utts == 0 || total_samples == 0) return PDS_OK;
+  PDS_REQUIRE(d_in && d_out && d_in != d_out && d_sig_off && d_sig_len, "null or aliased buffer");
+  PDS_REQUIRE(n_utts <= 65535, "at most 65535 utterances per call");
+  const long long per_utt = std::max<long long>(1, total_samples / n_utts);
+  dim3 grid((unsigned)std::min<long long>(64, (per_utt + 1023) / 1024), (unsigned)n_utts);
+  preemph_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_in, d_out, reinterpret_cast<const long long*>(d_sig_off),
+      reinterpret_cast<const long long*>(d_sig_len), coeff);
+  PDS_CUDA_CHECK(cudaGetLastError());
+  return PDS_OK;
+}
+
+extern "C" int pds_dither(const float* d_in, float* d_out, int64_t n_utts, const int64_t* d_sig_off,
+                          const int64_t* d_sig_len, int64_t total_samples, float coeff,
+                          uint64_t seed, void* stream) {
+  PDS_REQUIRE(n_utts >= 0 && total_samples >= 0, "bad shape");
+  if (n_utts == 0 || total_samples == 0) return PDS_OK;
+  PDS_REQUIRE(d_in && d_out && d_sig_off && d_sig_len, "null buffer");
+  PDS_REQUIRE(n_utts <= 65535, "at most 65535 utterances per call");
+  const long long per_utt = std::max<long long>(1, total_samples / n_utts);
+  dim3 grid((unsigned)std::min<long long>(64, (per_utt + 1023) / 1024), (unsigned)n_utts);
+  dither_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_in, d_out, reinterpret_cast<const long long*>(d_sig_off),
+      reinterpret_cast<const long long*>(d_sig_len), coeff, seed);
+  PDS_CUDA_CHECK(cudaGetLastError());
+  return PDS_OK;
+}

@@ -1,0 +1,280 @@
+// si.cu -- short-integration frame computer (K3 of SURVEY.md).
+//
+// Reference semantics (compute.py:613-999, spec: tests/test_compute.py:129-176): zero-pad the
+// signal on the left by pad_left, convolve it with each (max_support-tap, possibly complex) FIR
+// filter, take |y|^2 or |y| per sample, and pool 2S samples every S with the integration window;
+// floor + log.
+//
+// This first version evaluates the FIR directly in time (the reference uses overlap-save FFTs):
+// every thread owns kSamplesPerThread consecutive output samples of one filter and slides the
+// signal through registers, so the inner loop is FFMA on registers with one broadcast
+// shared-memory load of the tap and one of the new sample per kSamplesPerThread*2 FMAs.  Pooling
+// is fused: |y|^p never leaves registers; partial window sums go to shared-memory accumulators.
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pds {
+
+constexpr int kSiThreads = 256;
+constexpr int kSiTileFrames = 8;        // frames per tile
+constexpr int kSiSamplesPerThread = 8;  // consecutive outputs per thread
+
+struct SiParams {
+  const float* sig;
+  const pds_tile* tiles;
+  long long n_tiles;
+  float* out;
+  const float* h_re;    // [C][M]
+  const float* h_im;    // [C][M] (unused if is_real)
+  const float* window;  // [2S]
+  int S, C, M, pad_left;
+  int use_log;
+  float log_floor;
+};
+
+// y index i of the full convolution reads padded samples i-k; padded index q maps to x[q - pad_left]
+template <bool REAL, bool POWER>
+__global__ void __launch_bounds__(kSiThreads, 2) si_direct_kernel(const __grid_constant__ SiParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int S = p.S, M = p.M, C = p.C;
+  const int ny_max = (kSiTileFrames + 1) * S;          // pooled samples per tile
+  const int nx_max = ny_max + M - 1 + kSiSamplesPerThread;  // signal span they depend on
+  float* s_x = smem;                                    // [nx_max]
+  float* s_w = s_x + ((nx_max + 3) & ~3);               // [2S]
+  float* s_acc = s_w + ((2 * S + 3) & ~3);              // [kSiTileFrames][C]
+  float2* s_h = reinterpret_cast<float2*>(s_acc + ((kSiTileFrames * C + 3) & ~3));  // [M] taps of one filter per warp
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kSiThreads / 32;
+  float2* my_h = s_h + warp * M;
+
+  for (int i = tid; i < 2 * S; i += kSiThreads) s_w[i] = p.window[i];
+
+  for (long long tile_idx = blockIdx.x; tile_idx < p.n_tiles; tile_idx += gridDim.x) {
+    const pds_tile tile = p.tiles[tile_idx];
+    const int nframes = tile.nframes;
+    const int ny = (nframes + 1) * S;
+    const long long y0 = tile.start;  // first pooled sample (index into the full convolution)
+    const int nx = ny + M - 1;
+    __syncthreads();
+    // s_x[j] = padded sample (y0 - (M-1) + j); zero outside the signal
+    for (int j = tid; j < nx + kSiSamplesPerThread; j += kSiThreads) {
+      const long long g = y0 - (M - 1) + j - p.pad_left;
+      s_x[j] = (g >= 0 && g < tile.sig_len && j < nx) ? p.sig[tile.sig_off + g] : 0.f;
+    }
+    for (int i = tid; i < kSiTileFrames * C; i += kSiThreads) s_acc[i] = 0.f;
+    __syncthreads();
+
+    // warp task = (filter c, chunk of 32*SPT consecutive samples)
+    const int chunk = 32 * kSiSamplesPerThread;
+    const int nchunks = (ny + chunk - 1) / chunk;
+    for (int c = warp; c < C; c += NW) {
+      __syncwarp();
+      for (int k = lane; k < M; k += 32)
+        my_h[k] = make_float2(p.h_re[c * M + k], REAL ? 0.f : p.h_im[c * M + k]);
+      __syncwarp();
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int i0 = ch * chunk + lane * kSiSamplesPerThread;  // first output of this thread
+        // y[i0 + s] = sum_k h[k] * xs[(i0 + s) + (M-1) - k]; slide from k = M-1 down to 0
+        float re[kSiSamplesPerThread], im[kSiSamplesPerThread], xw[kSiSamplesPerThread];
+#pragma unroll
+        for (int s = 0; s < kSiSamplesPerThread; ++s) re[s] = 0.f, im[s] = 0.f;
+        // window of samples xs[i0 + s + (M-1) - k] for s = 0..SPT-1; start at k = M-1 -> xs[i0 + s]
+        const float* xs = s_x + min(i0, nx);  // clamp keeps idle lanes in bounds
+#pragma unroll
+        for (int s = 0; s < kSiSamplesPerThread; ++s) xw[s] = xs[s];
+        int k = M - 1;
+        int next = kSiSamplesPerThread;  // next sample to shift in: xs[next]
+        for (; k >= 0; --k) {
+          const float2 h = my_h[k];
+#pragma unroll
+          for (int s = 0; s < kSiSamplesPerThread; ++s) {
+            re[s] = fmaf(h.x, xw[s], re[s]);
+            if (!REAL) im[s] = fmaf(h.y, xw[s], im[s]);
+          }
+          // advance: k -> k-1 means every output reads one sample later
+#pragma unroll
+          for (int s = 0; s + 1 < kSiSamplesPerThread; ++s) xw[s] = xw[s + 1];
+          xw[kSiSamplesPerThread - 1] = (i0 + next < nx + kSiSamplesPerThread) ? xs[next] : 0.f;
+          ++next;
+        }
+        // pooling: sample r = i0 + s feeds frame t = r / S (window half 0) and t - 1 (half 1)
+#pragma unroll
+        for (int s = 0; s < kSiSamplesPerThread; ++s) {
+          const int r = i0 + s;
+          if (r < ny) {
+            float u = REAL ? re[s] * re[s] : re[s] * re[s] + im[s] * im[s];
+            if (!POWER) u = sqrtf(u);
+            const int t = r / S, n = r - t * S;
+            if (t < nframes) atomicAdd(&s_acc[t * C + c], s_w[n] * u);
+            if (t >= 1 && t - 1 < nframes) atomicAdd(&s_acc[(t - 1) * C + c], s_w[S + n] * u);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    float* __restrict__ dst = p.out + tile.out_row * C;
+    for (int i = tid; i < nframes * C; i += kSiThreads) {
+      float v = s_acc[i];
+      if (p.use_log) v = __logf(fmaxf(v, p.log_floor));
+      dst[i] = v;
+    }
+  }
+}
+
+}  // namespace pds
+
+using namespace pds;
+
+struct pds_si_plan {
+  int device = 0;
+  int S = 0, C = 0, M = 0, pad_left = 0, frame_start = 0, frames_lost = 0;
+  bool real = false, power = false;
+  size_t smem_bytes = 0;
+  int grid_limit = 0;
+  SiParams params{};
+  void* d_blob = nullptr;
+};
+
+namespace {
+using SiKernel = void (*)(const SiParams);
+SiKernel pick_si(const pds_si_plan* plan) {
+  if (plan->real) return plan->power ? si_direct_kernel<true, true> : si_direct_kernel<true, false>;
+  return plan->power ? si_direct_kernel<false, true> : si_direct_kernel<false, false>;
+}
+}  // namespace
+
+extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan** out) {
+  if (out) *out = nullptr;
+  PDS_REQUIRE(d && out, "null descriptor or output pointer");
+  PDS_REQUIRE(d->frame_shift >= 1 && d->num_filts >= 1 && d->max_support >= 1, "bad SI geometry");
+  PDS_REQUIRE(d->pad_left >= 0 && d->frame_start >= 0 && d->frames_lost >= 0, "bad SI offsets");
+  PDS_REQUIRE(d->h_real && d->window && (d->is_real || d->h_imag), "null table");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device || device < 0) {
+    cudaGetLastError();
+    set_error("no usable CUDA device %d (found %d); this library has no CPU fallback", device, ndev);
+    return PDS_ERR_CUDA;
+  }
+  PDS_CUDA_CHECK(cudaSetDevice(device));
+  pds_si_plan* plan = new (std::nothrow) pds_si_plan();
+  if (!plan) return PDS_ERR_NOMEM;
+  plan->device = device;
+  plan->S = d->frame_shift, plan->C = d->num_filts, plan->M = d->max_support;
+  plan->pad_left = d->pad_left, plan->frame_start = d->frame_start, plan->frames_lost = d->frames_lost;
+  plan->real = d->is_real != 0, plan->power = d->use_power != 0;
+  const size_t nh = (size_t)plan->C * plan->M;
+  const size_t o_re = 0, o_im = nh * sizeof(float), o_w = 2 * nh * sizeof(float);
+  const size_t bytes = o_w + 2 * (size_t)plan->S * sizeof(float);
+  std::vector<unsigned char> blob(bytes, 0);
+  memcpy(blob.data() + o_re, d->h_real, nh * sizeof(float));
+  if (!plan->real) memcpy(blob.data() + o_im, d->h_imag, nh * sizeof(float));
+  memcpy(blob.data() + o_w, d->window, 2 * (size_t)plan->S * sizeof(float));
+  cudaError_t err = cudaMalloc(&plan->d_blob, bytes);
+  if (err == cudaSuccess) err = cudaMemcpy(plan->d_blob, blob.data(), bytes, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    set_error("uploading SI tables failed: %s", cudaGetErrorString(err));
+    pds_si_plan_destroy(plan);
+    return PDS_ERR_CUDA;
+  }
+  unsigned char* base = static_cast<unsigned char*>(plan->d_blob);
+  SiParams& p = plan->params;
+  p.h_re = reinterpret_cast<const float*>(base + o_re);
+  p.h_im = reinterpret_cast<const float*>(base + o_im);
+  p.window = reinterpret_cast<const float*>(base + o_w);
+  p.S = plan->S, p.C = plan->C, p.M = plan->M, p.pad_left = plan->pad_left;
+  p.use_log = d->use_log ? 1 : 0;
+  p.log_floor = d->log_floor;
+  const int S = plan->S, M = plan->M, C = plan->C;
+  const int ny_max = (kSiTileFrames + 1) * S, nx_max = ny_max + M - 1 + kSiSamplesPerThread;
+  plan->smem_bytes = sizeof(float) * (size_t)(((nx_max + 3) & ~3) + ((2 * S + 3) & ~3) +
+                                             ((kSiTileFrames * C + 3) & ~3)) +
+                     sizeof(float2) * (size_t)M * (kSiThreads / 32);
+  cudaDeviceProp prop;
+  err = cudaGetDeviceProperties(&prop, device);
+  if (err != cudaSuccess || plan->smem_bytes > prop.sharedMemPerBlockOptin) {
+    set_error("SI geometry (S=%d, max_support=%d, %d filters) needs %zu bytes of shared memory", S,
+              M, C, plan->smem_bytes);
+    pds_si_plan_destroy(plan);
+    return err != cudaSuccess ? PDS_ERR_CUDA : PDS_ERR_UNSUPPORTED;
+  }
+  err = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_si(plan)),
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+  if (err != cudaSuccess) {
+    set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(err));
+    pds_si_plan_destroy(plan);
+    return PDS_ERR_CUDA;
+  }
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(pick_si(plan)),
+                                                kSiThreads, plan->smem_bytes);
+  plan->grid_limit = prop.multiProcessorCount * std::max(1, occ);
+  *out = plan;
+  return PDS_OK;
+}
+
+extern "C" void pds_si_plan_destroy(pds_si_plan* plan) {
+  if (!plan) return;
+  cudaSetDevice(plan->device);
+  if (plan->d_blob) cudaFree(plan->d_blob);
+  delete plan;
+}
+
+extern "C" int64_t pds_si_num_frames(const pds_si_plan* plan, int64_t sig_len) {
+  if (!plan) return 0;
+  const int64_t t = (sig_len + plan->S / 2) / plan->S - plan->frames_lost;
+  return t > 0 ? t : 0;
+}
+
+extern "C" int pds_si_tile_frames(const pds_si_plan*) { return kSiTileFrames; }
+
+extern "C" int pds_si_layout(const pds_si_plan* plan, int64_t n_utts, const int64_t* sig_len,
+                             int64_t* frame_off, int64_t* n_tiles) {
+  PDS_REQUIRE(plan && sig_len && frame_off && n_tiles && n_utts >= 0, "bad argument");
+  int64_t rows = 0, tiles = 0;
+  for (int64_t u = 0; u < n_utts; ++u) {
+    PDS_REQUIRE(sig_len[u] >= 0 && sig_len[u] < ((int64_t)1 << 31) - (1 << 20), "utterance %lld too long",
+                (long long)u);
+    frame_off[u] = rows;
+    const int64_t t = pds_si_num_frames(plan, sig_len[u]);
+    rows += t;
+    tiles += (t + kSiTileFrames - 1) / kSiTileFrames;
+  }
+  frame_off[n_utts] = rows;
+  *n_tiles = tiles;
+  return PDS_OK;
+}
+
+extern "C" int pds_si_fill_tiles(const pds_si_plan* plan, int64_t n_utts, const int64_t* sig_off,
+                                 const int64_t* sig_len, const int64_t* frame_off, pds_tile* tiles) {
+  PDS_REQUIRE(plan && sig_off && sig_len && frame_off && (tiles || n_utts == 0), "bad argument");
+  int64_t n = 0;
+  for (int64_t u = 0; u < n_utts; ++u) {
+    const int64_t t_total = frame_off[u + 1] - frame_off[u];
+    for (int64_t t0 = 0; t0 < t_total; t0 += kSiTileFrames) {
+      pds_tile& tile = tiles[n++];
+      tile.sig_off = sig_off[u];
+      tile.sig_len = (int32_t)sig_len[u];
+      tile.start = (int32_t)(plan->frame_start + t0 * plan->S);
+      tile.nframes = (int32_t)std::min<int64_t>(kSiTileFrames, t_total - t0);
+      tile.utt = (int32_t)u;
+      tile.out_row = frame_off[u] + t0;
+    }
+  }
+  return PDS_OK;
+}
+
+extern "C" int pds_si_run(pds_si_plan* plan, const float* d_signal, const pds_tile* d_tiles,
+                          int64_t n_tiles, float* d_out, void* stream) {
+  PDS_REQUIRE(plan, "null plan");
+  if (n_tiles == 0) return PDS_OK;
+  PDS_REQUIRE(d_signal && d_tiles && d_out && n_tiles > 0, "null buffer");
+  SiParams p = plan->params;
+  p.sig = d_signal, p.tiles = d_tiles, p.n_tiles = n_tiles, p.out = d_out;
+  const int grid = (int)std::min<int64_t>(n_tiles, plan->grid_limit);
+  pick_si(plan)<<<grid, kSiThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+  PDS_CUDA_CHECK(cudaGetLastError());
+  return PDS_OK;
+}

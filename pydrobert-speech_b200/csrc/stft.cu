@@ -1,0 +1,807 @@
+// stft.cu -- the fused STFT frame-feature kernel (K1+K2 of SURVEY.md) and its C ABI.
+//
+// One persistent CTA (256 threads) walks a list of tiles; a tile is up to TF = 32 consecutive
+// frames of one utterance.  Per tile:
+//
+//   stage   : the contiguous span of samples the tile touches ((nframes-1)*S + L floats) is
+//             copied once from HBM to shared memory (128-bit loads when the span is interior
+//             and aligned), with symmetric reflection at the utterance edges and, optionally,
+//             dither and pre-emphasis applied on the way (pre.py:90-149).
+//   fft     : sub-groups of G lanes each take a frame: window multiply, raw-frame energy,
+//             R1-point in-register DFT, twiddle, one shared-memory exchange, G-point DFT(s),
+//             real-FFT split through warp shuffles, |X|^2 (or |X|) -> s_P[bin][frame].
+//   bank    : lane = frame, warp = subset of filters: banded dot product of the power
+//             spectrum with the folded weights (compute.py:416-457), floor + log.
+//   store   : the (nframes x C) block is contiguous in the packed output; coalesced copy.
+//
+// Geometry outside the shared-memory FFT's reach (non power-of-two N, odd S, ...) runs through
+// stft_direct_kernel, a plain O(L*K) DFT per frame with the same staging and bank code.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "fft_core.cuh"
+
+namespace pds {
+
+constexpr int kThreads = 256;
+constexpr int kTileFrames = 32;       // frames per tile on the FFT path (= lanes of the bank phase)
+constexpr int kTileStride = 34;       // s_P row stride; 34 = 2 (mod 32) keeps both phases conflict free
+constexpr int kDirectTileFrames = 4;  // frames per tile on the direct-DFT path
+constexpr int kDirectThreads = 128;
+
+struct StftParams {
+  const void* sig;
+  const pds_tile* tiles;
+  long long n_tiles;
+  float* out;
+  const float* window;      // [N] zero padded; pre-scaled by 1/2 on the FFT path
+  const float2* tw_stage;   // [G][R1]  W_NC^(l*k1)
+  const float2* tw_split;   // [G][R1/2] W_N^(l + G*m)
+  const float2* tw_direct;  // [N] e^{-2 pi i j / N} (direct path only)
+  const int* band_lo;       // [F]
+  const int* band_n4;       // [F] taps / 4 after zero padding to a multiple of 4
+  const int* band_off;      // [F] offset (floats, multiple of 4) into weights
+  const float* weights;     // padded taps
+  int weights_total;        // floats in `weights`
+  int weights_in_smem;
+  int L, S, N, K, F, C;
+  int rows_full, row_partial;  // L / (2G) full rows of the stage-1 load, and whether one more is partial
+  int span_max;                // floats reserved for the staged samples
+  int include_energy, use_log;
+  float log_floor, inv_L, preemph, dither;
+  int dither_first;
+  unsigned long long seed;
+};
+
+// ------------------------------------------------------------------------------------------
+// sample staging
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float preprocessed_sample(const T* __restrict__ sig, long long base,
+                                                     long long g, const StftParams& p, int utt) {
+  float x = load_sample(sig, base + g);
+  if (p.dither != 0.f && p.dither_first) x += p.dither * philox_normal(p.seed, utt, g);
+  if (p.preemph != 0.f && g > 0) {
+    float prev = load_sample(sig, base + g - 1);
+    if (p.dither != 0.f && p.dither_first) prev += p.dither * philox_normal(p.seed, utt, g - 1);
+    x -= p.preemph * prev;
+  }
+  if (p.dither != 0.f && !p.dither_first) x += p.dither * philox_normal(p.seed, utt, g);
+  return x;
+}
+
+template <typename T, int THREADS>
+__device__ __forceinline__ void stage_samples(float* __restrict__ s_x, const StftParams& p,
+                                              const pds_tile& tile, int span) {
+  const T* __restrict__ sig = static_cast<const T*>(p.sig);
+  const int tid = threadIdx.x;
+  const long long first = tile.start;
+  const bool interior = first >= 0 && first + span <= (long long)tile.sig_len;
+  const bool plain = p.dither == 0.f && p.preemph == 0.f;
+  if (sizeof(T) == 4 && interior && plain &&
+      ((reinterpret_cast<uintptr_t>(sig + tile.sig_off + first) & 15u) == 0)) {
+    // interior + aligned: straight 128-bit copy, read-only path, no L1 allocation
+    const float4* __restrict__ src = reinterpret_cast<const float4*>(sig + tile.sig_off + first);
+    float4* dst = reinterpret_cast<float4*>(s_x);
+    const int n4 = span >> 2;
+    for (int i = tid; i < n4; i += THREADS) {
+      float4 v;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                   : "l"(src + i));
+      dst[i] = v;
+    }
+    for (int i = (n4 << 2) + tid; i < span; i += THREADS)
+      s_x[i] = load_sample(sig, tile.sig_off + first + i);
+    return;
+  }
+  for (int i = tid; i < span; i += THREADS) {
+    const long long g = reflect_index(first + i, tile.sig_len);
+    s_x[i] = preprocessed_sample(sig, tile.sig_off, g, p, tile.utt);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// filter-bank phase: lane = frame, each warp takes every (blockDim/32)-th filter
+// ------------------------------------------------------------------------------------------
+template <int THREADS, int STRIDE>
+__device__ __forceinline__ void bank_phase(const float* __restrict__ s_P,
+                                           const float* __restrict__ s_e,
+                                           float* __restrict__ s_out,
+                                           const float* __restrict__ weights,
+                                           const int* __restrict__ s_lo,
+                                           const int* __restrict__ s_n4,
+                                           const int* __restrict__ s_off, const StftParams& p,
+                                           bool power) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e_off = p.include_energy;
+  for (int f = warp; f < p.F; f += THREADS / 32) {
+    const float4* __restrict__ wt = reinterpret_cast<const float4*>(weights + s_off[f]);
+    const float* __restrict__ pp = s_P + s_lo[f] * STRIDE + lane;
+    const int n4 = s_n4[f];
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int j = 0; j < n4; ++j) {
+      const float4 w = wt[j];
+      acc0 = fmaf(pp[0], w.x, acc0);
+      acc1 = fmaf(pp[STRIDE], w.y, acc1);
+      acc0 = fmaf(pp[2 * STRIDE], w.z, acc0);
+      acc1 = fmaf(pp[3 * STRIDE], w.w, acc1);
+      pp += 4 * STRIDE;
+    }
+    float v = acc0 + acc1;
+    if (p.use_log) v = __logf(fmaxf(v, p.log_floor));
+    s_out[lane * p.C + e_off + f] = v;
+  }
+  if (p.include_energy && warp == 0) {
+    float v = s_e[lane] * p.inv_L;
+    if (!power) v = sqrtf(v);
+    if (p.use_log) v = __logf(fmaxf(v, p.log_floor));
+    s_out[lane * p.C] = v;
+  }
+}
+
+// shared-memory carve-up shared by host (size computation) and device
+struct SmemLayout {
+  int x, w, scr, P, e, lo, n4, off, wt, total;  // offsets in floats; total in bytes
+};
+
+__host__ __device__ inline int take_floats(int& cursor, int n) {
+  const int at = cursor;
+  cursor += (n + 3) & ~3;  // keep every region 16-byte aligned
+  return at;
+}
+
+__host__ __device__ inline SmemLayout fused_layout(int N, int G, int R1, int span_max, int F,
+                                                   int weights_floats) {
+  SmemLayout s;
+  const int K = N / 2 + 1;
+  int o = 0;
+  s.x = take_floats(o, span_max + 64);  // + zeroed slack past the last staged sample
+  s.w = take_floats(o, N);
+  s.scr = take_floats(o, 2 * (kThreads / G) * G * (R1 + 1));
+  s.P = take_floats(o, (K + 7) * kTileStride);  // + zero rows read by the 4-tap band padding
+  s.e = take_floats(o, kTileFrames);
+  s.lo = take_floats(o, F);
+  s.n4 = take_floats(o, F);
+  s.off = take_floats(o, F);
+  s.wt = take_floats(o, weights_floats);
+  s.total = o * 4;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// the fused kernel
+// ------------------------------------------------------------------------------------------
+template <int N, bool POWER, typename T>
+__global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
+    stft_fused_kernel(const __grid_constant__ StftParams p) {
+  using Geo = FftGeom<N>;
+  constexpr int NC = Geo::NC, G = Geo::G, R1 = Geo::R1, NSUB = Geo::NSUB;
+  constexpr int K = NC + 1;
+  constexpr int FPR = kThreads / G;  // frames per round
+  constexpr bool REGTW = (R1 <= 16);
+  constexpr int TS = kTileStride;
+
+  extern __shared__ __align__(16) float smem[];
+  const SmemLayout lay = fused_layout(N, G, R1, p.span_max, p.F, p.weights_in_smem ? p.weights_total : 0);
+  float* s_x = smem + lay.x;
+  float* s_w = smem + lay.w;
+  float2* s_scr = reinterpret_cast<float2*>(smem + lay.scr);
+  float* s_P = smem + lay.P;
+  float* s_e = smem + lay.e;
+  int* s_lo = reinterpret_cast<int*>(smem + lay.lo);
+  int* s_n4 = reinterpret_cast<int*>(smem + lay.n4);
+  int* s_off = reinterpret_cast<int*>(smem + lay.off);
+  float* s_wt = smem + lay.wt;
+  float* s_out = s_x;  // the staged samples are dead once the fft phase is over
+
+  const int tid = threadIdx.x;
+  const int sub = tid / G, l = tid % G;
+
+  // ---- one-time CTA set-up -------------------------------------------------------------
+  for (int i = tid; i < N; i += kThreads) s_w[i] = p.window[i];
+  for (int i = tid; i < p.F; i += kThreads) {
+    s_lo[i] = p.band_lo[i];
+    s_n4[i] = p.band_n4[i];
+    s_off[i] = p.band_off[i];
+  }
+  if (p.weights_in_smem)
+    for (int i = tid; i < p.weights_total; i += kThreads) s_wt[i] = p.weights[i];
+  for (int i = tid; i < 7 * TS; i += kThreads) s_P[K * TS + i] = 0.f;  // padding rows
+  for (int i = tid; i < 64; i += kThreads) s_x[p.span_max + i] = 0.f;
+  const float* bank_weights = p.weights_in_smem ? s_wt : p.weights;
+
+  float2 tw_stage[REGTW ? R1 : 1], tw_split[REGTW ? R1 / 2 : 1];
+  if (REGTW) {
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) tw_stage[k1] = p.tw_stage[l * R1 + k1];
+#pragma unroll
+    for (int m = 0; m < R1 / 2; ++m) tw_split[m] = p.tw_split[l * (R1 / 2) + m];
+  }
+  const int partner = (G - l) % G;
+  float2* scr = s_scr + sub * Geo::SCR_FLOAT2;
+  __syncthreads();
+
+  for (long long tile_idx = blockIdx.x; tile_idx < p.n_tiles; tile_idx += gridDim.x) {
+    const pds_tile tile = p.tiles[tile_idx];
+    const int nframes = tile.nframes;
+    const int span = (nframes - 1) * p.S + p.L;
+
+    stage_samples<T, kThreads>(s_x, p, tile, span);
+    __syncthreads();
+
+    // ---- fft phase ---------------------------------------------------------------------
+    for (int t0 = 0; t0 < nframes; t0 += FPR) {
+      // sub-groups past the end recompute the last frame (identical writes) so that the
+      // shuffles below always run with full warps
+      const int t = min(t0 + sub, nframes - 1);
+      const float* fx = s_x + t * p.S;
+      const float2* xp = reinterpret_cast<const float2*>(fx) + l;
+      const float2* wp = reinterpret_cast<const float2*>(s_w) + l;
+      float2 z[R1];
+      float energy = 0.f;
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        if (r < p.rows_full) {
+          const float2 x = xp[G * r], w = wp[G * r];
+          energy = fmaf(x.x, x.x, energy);
+          energy = fmaf(x.y, x.y, energy);
+          z[r] = make_float2(x.x * w.x, x.y * w.y);
+        } else if (r == p.rows_full && p.row_partial) {
+          const int i0 = 2 * (G * r + l);
+          const float x0 = i0 < p.L ? fx[i0] : 0.f;
+          const float x1 = i0 + 1 < p.L ? fx[i0 + 1] : 0.f;
+          const float2 w = wp[G * r];
+          energy = fmaf(x0, x0, energy);
+          energy = fmaf(x1, x1, energy);
+          z[r] = make_float2(x0 * w.x, x1 * w.y);
+        } else {
+          z[r] = make_float2(0.f, 0.f);
+        }
+      }
+      if (p.include_energy) {
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) energy += __shfl_xor_sync(0xffffffffu, energy, off, G);
+        if (l == 0) s_e[t] = energy;
+      }
+
+      Dft<R1>::run(z);
+#pragma unroll
+      for (int k1 = 1; k1 < R1; ++k1)
+        z[k1] = cmul(z[k1], REGTW ? tw_stage[k1] : __ldg(&p.tw_stage[l * R1 + k1]));
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) scr[l * Geo::SCR_STRIDE + k1] = z[k1];
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < NSUB; ++j) {
+        float2 v[G];
+#pragma unroll
+        for (int n2 = 0; n2 < G; ++n2) v[n2] = scr[n2 * Geo::SCR_STRIDE + l + G * j];
+        Dft<G>::run(v);
+#pragma unroll
+        for (int k2 = 0; k2 < G; ++k2) z[j + NSUB * k2] = v[k2];
+      }
+      __syncwarp();
+
+      // real-FFT split: lane l pairs its lower-half registers with the partner's upper half
+      float* pcol = s_P + t;
+#pragma unroll
+      for (int m = 0; m < R1 / 2; ++m) {
+        float2 b;
+        b.x = __shfl_sync(0xffffffffu, z[R1 - 1 - m].x, partner, G);
+        b.y = __shfl_sync(0xffffffffu, z[R1 - 1 - m].y, partner, G);
+        if (l == 0) b = z[(R1 - m) % R1];
+        const float2 w = REGTW ? tw_split[m] : __ldg(&p.tw_split[l * (R1 / 2) + m]);
+        float2 xk, xq;
+        split_pair(z[m], b, w, xk, xq);
+        float pk = xk.x * xk.x + xk.y * xk.y, pq = xq.x * xq.x + xq.y * xq.y;
+        if (!POWER) {
+          pk = sqrtf(pk);
+          pq = sqrtf(pq);
+        }
+        const int k = l + G * m;
+        pcol[k * TS] = pk;
+        pcol[(NC - k) * TS] = pq;
+      }
+      if (l == 0) {  // bin NC/2 pairs with itself; its twiddle is -i
+        const float2 a = z[R1 / 2];
+        float2 xk, xq;
+        split_pair(a, a, make_float2(0.f, -1.f), xk, xq);
+        float pk = xk.x * xk.x + xk.y * xk.y;
+        if (!POWER) pk = sqrtf(pk);
+        pcol[(NC / 2) * TS] = pk;
+      }
+    }
+    __syncthreads();
+
+    // ---- filter bank + log -------------------------------------------------------------
+    bank_phase<kThreads, TS>(s_P, s_e, s_out, bank_weights, s_lo, s_n4, s_off, p, POWER);
+    __syncthreads();
+
+    // ---- coalesced store ---------------------------------------------------------------
+    float* __restrict__ dst = p.out + tile.out_row * p.C;
+    const int total = nframes * p.C;
+    for (int i = tid; i < total; i += kThreads) dst[i] = s_out[i];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic fallback: direct DFT, any N / L / S
+// ------------------------------------------------------------------------------------------
+template <bool POWER, typename T>
+__global__ void __launch_bounds__(kDirectThreads)
+    stft_direct_kernel(const __grid_constant__ StftParams p) {
+  extern __shared__ __align__(16) float smem[];
+  // layout: frame [L] | twiddles [2N] | P [K + 7] | energy scratch [4]
+  float* s_f = smem;
+  float2* s_tw = reinterpret_cast<float2*>(smem + ((p.L + 3) & ~3));
+  float* s_P = reinterpret_cast<float*>(s_tw + p.N);
+  float* s_red = s_P + ((p.K + 7 + 3) & ~3);
+  const int tid = threadIdx.x;
+  const T* __restrict__ sig = static_cast<const T*>(p.sig);
+  for (int i = tid; i < p.N; i += kDirectThreads) s_tw[i] = p.tw_direct[i];
+  for (int i = tid; i < 7; i += kDirectThreads) s_P[p.K + i] = 0.f;
+  __syncthreads();
+
+  for (long long tile_idx = blockIdx.x; tile_idx < p.n_tiles; tile_idx += gridDim.x) {
+    const pds_tile tile = p.tiles[tile_idx];
+    for (int t = 0; t < tile.nframes; ++t) {
+      // windowed frame + raw energy
+      float e = 0.f;
+      for (int i = tid; i < p.L; i += kDirectThreads) {
+        const long long g = reflect_index((long long)tile.start + (long long)t * p.S + i, tile.sig_len);
+        const float x = preprocessed_sample(sig, tile.sig_off, g, p, tile.utt);
+        e = fmaf(x, x, e);
+        s_f[i] = x * p.window[i];
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+      if ((tid & 31) == 0) s_red[tid >> 5] = e;
+      __syncthreads();
+      for (int k = tid; k < p.K; k += kDirectThreads) {
+        float re = 0.f, im = 0.f;
+        int idx = 0;
+        for (int n = 0; n < p.L; ++n) {
+          const float2 w = s_tw[idx];
+          const float x = s_f[n];
+          re = fmaf(x, w.x, re);
+          im = fmaf(x, w.y, im);
+          idx += k;
+          if (idx >= p.N) idx -= p.N;
+        }
+        const float pw = re * re + im * im;
+        s_P[k] = POWER ? pw : sqrtf(pw);
+      }
+      __syncthreads();
+      float* __restrict__ dst = p.out + (tile.out_row + t) * p.C;
+      for (int f = tid; f < p.F; f += kDirectThreads) {
+        const float* wt = p.weights + p.band_off[f];
+        const float* pp = s_P + p.band_lo[f];
+        const int n = p.band_n4[f] * 4;
+        float acc = 0.f;
+        for (int j = 0; j < n; ++j) acc = fmaf(pp[j], wt[j], acc);
+        if (p.use_log) acc = __logf(fmaxf(acc, p.log_floor));
+        dst[p.include_energy + f] = acc;
+      }
+      if (p.include_energy && tid == 0) {
+        float v = 0.f;
+        for (int w = 0; w < kDirectThreads / 32; ++w) v += s_red[w];
+        v *= p.inv_L;
+        if (!POWER) v = sqrtf(v);
+        if (p.use_log) v = __logf(fmaxf(v, p.log_floor));
+        dst[0] = v;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace pds
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+using namespace pds;
+
+struct pds_stft_plan {
+  int device = 0;
+  int L = 0, S = 0, N = 0, K = 0, F = 0, C = 0, pad_left = 0;
+  bool fast = false;
+  bool power = false;
+  int tile_frames = 0;
+  int G = 0, R1 = 0;
+  size_t smem_bytes = 0;
+  int grid_limit = 0;
+  StftParams params{};
+  void* d_blob = nullptr;  // all constant tables, one allocation
+  // scratch for pds_stft_compute_host
+  void* d_sig = nullptr;
+  size_t d_sig_bytes = 0;
+  pds_tile* d_tiles = nullptr;
+  size_t d_tiles_cap = 0;
+  float* d_out = nullptr;
+  size_t d_out_bytes = 0;
+};
+
+namespace {
+
+using KernelFn = void (*)(const StftParams);
+
+template <int N>
+KernelFn pick_fused(bool power, int dtype) {
+  if (power) {
+    if (dtype == PDS_F32) return stft_fused_kernel<N, true, float>;
+    if (dtype == PDS_I16) return stft_fused_kernel<N, true, short>;
+    return stft_fused_kernel<N, true, double>;
+  }
+  if (dtype == PDS_F32) return stft_fused_kernel<N, false, float>;
+  if (dtype == PDS_I16) return stft_fused_kernel<N, false, short>;
+  return stft_fused_kernel<N, false, double>;
+}
+
+KernelFn pick_kernel(const pds_stft_plan* plan, int dtype) {
+  if (plan->fast) {
+    switch (plan->N) {
+      case 128: return pick_fused<128>(plan->power, dtype);
+      case 256: return pick_fused<256>(plan->power, dtype);
+      case 512: return pick_fused<512>(plan->power, dtype);
+      case 1024: return pick_fused<1024>(plan->power, dtype);
+      case 2048: return pick_fused<2048>(plan->power, dtype);
+      default: return nullptr;
+    }
+  }
+  if (plan->power) {
+    if (dtype == PDS_F32) return stft_direct_kernel<true, float>;
+    if (dtype == PDS_I16) return stft_direct_kernel<true, short>;
+    return stft_direct_kernel<true, double>;
+  }
+  if (dtype == PDS_F32) return stft_direct_kernel<false, float>;
+  if (dtype == PDS_I16) return stft_direct_kernel<false, short>;
+  return stft_direct_kernel<false, double>;
+}
+
+void geometry_for(int N, int* G, int* R1) {
+  const int NC = N / 2;
+  *G = NC >= 1024 ? 32 : (NC >= 256 ? 16 : (NC >= 64 ? 8 : 4));
+  *R1 = NC / *G;
+}
+
+size_t dtype_size(int dtype) { return dtype == PDS_I16 ? 2 : (dtype == PDS_F64 ? 8 : 4); }
+
+}  // namespace
+
+extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft_plan** out) {
+  if (out) *out = nullptr;
+  PDS_REQUIRE(d && out, "null descriptor or output pointer");
+  PDS_REQUIRE(d->frame_length >= 1 && d->frame_shift >= 1, "frame_length/frame_shift must be positive");
+  PDS_REQUIRE(d->dft_size >= d->frame_length, "dft_size (%d) < frame_length (%d)", d->dft_size,
+              d->frame_length);
+  PDS_REQUIRE(d->num_filts >= 1, "need at least one filter");
+  PDS_REQUIRE(d->pad_left >= 0, "pad_left must be non-negative");
+  PDS_REQUIRE(d->window && d->band_lo && d->band_len && d->band_off && d->weights, "null table");
+  const int N = d->dft_size, L = d->frame_length, S = d->frame_shift, F = d->num_filts;
+  const int K = N % 2 ? (N + 1) / 2 : N / 2 + 1;
+  for (int f = 0; f < F; ++f)
+    PDS_REQUIRE(d->band_lo[f] >= 0 && d->band_len[f] >= 0 && d->band_lo[f] + d->band_len[f] <= K,
+                "band %d = [%d, %d) outside the %d bins", f, d->band_lo[f],
+                d->band_lo[f] + d->band_len[f], K);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device || device < 0) {
+    cudaGetLastError();
+    set_error("no usable CUDA device %d (found %d); this library has no CPU fallback", device, ndev);
+    return PDS_ERR_CUDA;
+  }
+  PDS_CUDA_CHECK(cudaSetDevice(device));
+
+  pds_stft_plan* plan = new (std::nothrow) pds_stft_plan();
+  if (!plan) return PDS_ERR_NOMEM;
+  plan->device = device;
+  plan->L = L, plan->S = S, plan->N = N, plan->K = K, plan->F = F;
+  plan->C = F + (d->include_energy ? 1 : 0);
+  plan->pad_left = d->pad_left;
+  plan->power = d->use_power != 0;
+  cudaDeviceProp prop;
+  cudaError_t err = cudaGetDeviceProperties(&prop, device);
+  if (err != cudaSuccess) {
+    set_error("cudaGetDeviceProperties failed: %s", cudaGetErrorString(err));
+    delete plan;
+    return PDS_ERR_CUDA;
+  }
+  const size_t smem_cap = prop.sharedMemPerBlockOptin;
+
+  // band tables, zero padded to whole groups of four taps
+  std::vector<int> lo(F), n4(F), off(F);
+  int wtotal = 0;
+  for (int f = 0; f < F; ++f) {
+    lo[f] = d->band_lo[f];
+    n4[f] = (d->band_len[f] + 3) / 4;
+    off[f] = wtotal;
+    wtotal += n4[f] * 4;
+  }
+
+  // ---- pick the kernel: shared-memory FFT when the geometry allows, else direct DFT ------
+  StftParams& p = plan->params;
+  const bool pow2 = (N & (N - 1)) == 0;
+  plan->fast = pow2 && N >= 128 && N <= 2048 && (S % 2 == 0);
+  if (plan->fast) {
+    geometry_for(N, &plan->G, &plan->R1);
+    const int G = plan->G, R1 = plan->R1;
+    p.rows_full = L / (2 * G);
+    p.row_partial = (L % (2 * G)) != 0;
+    p.span_max = std::max((kTileFrames - 1) * S + L, kTileFrames * plan->C);  // s_out aliases s_x
+    // keep the weights in shared memory while that still leaves room for two CTAs per SM
+    const SmemLayout with = fused_layout(N, G, R1, p.span_max, F, wtotal);
+    const SmemLayout without = fused_layout(N, G, R1, p.span_max, F, 0);
+    p.weights_in_smem = (size_t)with.total <= std::min<size_t>(smem_cap, 110 * 1024) ? 1 : 0;
+    plan->smem_bytes = p.weights_in_smem ? with.total : without.total;
+    if (plan->smem_bytes > smem_cap) plan->fast = false;  // huge frame shift: use the direct kernel
+  }
+  if (!plan->fast) {
+    plan->smem_bytes = sizeof(float) * (((L + 3) & ~3) + 2 * (size_t)N + ((K + 7 + 3) & ~3) + 8);
+    if (plan->smem_bytes > smem_cap) {
+      set_error("dft_size %d needs %zu bytes of shared memory (> %zu)", N, plan->smem_bytes, smem_cap);
+      delete plan;
+      return PDS_ERR_UNSUPPORTED;
+    }
+  }
+  plan->tile_frames = plan->fast ? kTileFrames : kDirectTileFrames;
+
+  // ---- build the constant tables on the host (double precision trig) --------------------
+  std::vector<float> wt(std::max(wtotal, 4), 0.f);
+  for (int f = 0; f < F; ++f)
+    for (int j = 0; j < d->band_len[f]; ++j) wt[off[f] + j] = d->weights[d->band_off[f] + j];
+  std::vector<float> win(N, 0.f);
+  for (int i = 0; i < L; ++i) win[i] = plan->fast ? 0.5f * d->window[i] : d->window[i];
+  const double two_pi = 6.283185307179586476925286766559;
+  std::vector<float2> tw_stage, tw_split, tw_direct;
+  if (plan->fast) {
+    const int G = plan->G, R1 = plan->R1, NC = N / 2;
+    tw_stage.resize((size_t)G * R1);
+    for (int l = 0; l < G; ++l)
+      for (int k1 = 0; k1 < R1; ++k1) {
+        const double a = -two_pi * (double)((long long)l * k1 % NC) / NC;
+        tw_stage[(size_t)l * R1 + k1] = make_float2((float)std::cos(a), (float)std::sin(a));
+      }
+    tw_split.resize((size_t)G * (R1 / 2));
+    for (int l = 0; l < G; ++l)
+      for (int m = 0; m < R1 / 2; ++m) {
+        const double a = -two_pi * (double)(l + G * m) / N;
+        tw_split[(size_t)l * (R1 / 2) + m] = make_float2((float)std::cos(a), (float)std::sin(a));
+      }
+  } else {
+    tw_direct.resize(N);
+    for (int j = 0; j < N; ++j) {
+      const double a = -two_pi * j / N;
+      tw_direct[j] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+  }
+
+  // ---- one device blob -----------------------------------------------------------------
+  auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  size_t o_win = 0, o_tws = align16(o_win + sizeof(float) * N);
+  size_t o_twp = align16(o_tws + sizeof(float2) * tw_stage.size());
+  size_t o_twd = align16(o_twp + sizeof(float2) * tw_split.size());
+  size_t o_lo = align16(o_twd + sizeof(float2) * tw_direct.size());
+  size_t o_n4 = align16(o_lo + sizeof(int) * F);
+  size_t o_off = align16(o_n4 + sizeof(int) * F);
+  size_t o_wt = align16(o_off + sizeof(int) * F);
+  size_t blob_bytes = align16(o_wt + sizeof(float) * wt.size());
+  std::vector<unsigned char> blob(blob_bytes, 0);
+  std::memcpy(blob.data() + o_win, win.data(), sizeof(float) * N);
+  if (!tw_stage.empty()) std::memcpy(blob.data() + o_tws, tw_stage.data(), sizeof(float2) * tw_stage.size());
+  if (!tw_split.empty()) std::memcpy(blob.data() + o_twp, tw_split.data(), sizeof(float2) * tw_split.size());
+  if (!tw_direct.empty()) std::memcpy(blob.data() + o_twd, tw_direct.data(), sizeof(float2) * tw_direct.size());
+  std::memcpy(blob.data() + o_lo, lo.data(), sizeof(int) * F);
+  std::memcpy(blob.data() + o_n4, n4.data(), sizeof(int) * F);
+  std::memcpy(blob.data() + o_off, off.data(), sizeof(int) * F);
+  std::memcpy(blob.data() + o_wt, wt.data(), sizeof(float) * wt.size());
+  err = cudaMalloc(&plan->d_blob, blob_bytes);
+  if (err == cudaSuccess) err = cudaMemcpy(plan->d_blob, blob.data(), blob_bytes, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    set_error("uploading plan tables failed: %s", cudaGetErrorString(err));
+    pds_stft_plan_destroy(plan);
+    return PDS_ERR_CUDA;
+  }
+  unsigned char* base = static_cast<unsigned char*>(plan->d_blob);
+  p.window = reinterpret_cast<const float*>(base + o_win);
+  p.tw_stage = reinterpret_cast<const float2*>(base + o_tws);
+  p.tw_split = reinterpret_cast<const float2*>(base + o_twp);
+  p.tw_direct = reinterpret_cast<const float2*>(base + o_twd);
+  p.band_lo = reinterpret_cast<const int*>(base + o_lo);
+  p.band_n4 = reinterpret_cast<const int*>(base + o_n4);
+  p.band_off = reinterpret_cast<const int*>(base + o_off);
+  p.weights = reinterpret_cast<const float*>(base + o_wt);
+  p.weights_total = wtotal;
+  p.L = L, p.S = S, p.N = N, p.K = K, p.F = F, p.C = plan->C;
+  p.include_energy = d->include_energy ? 1 : 0;
+  p.use_log = d->use_log ? 1 : 0;
+  p.log_floor = d->log_floor;
+  p.inv_L = 1.0f / (float)L;
+  p.preemph = d->preemph;
+  p.dither = d->dither;
+  p.dither_first = d->dither_first ? 1 : 0;
+
+  // opt in to the dynamic shared memory for every instantiation this plan may launch
+  for (int dt = 0; dt < 3; ++dt) {
+    KernelFn fn = pick_kernel(plan, dt);
+    err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+    if (err != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", plan->smem_bytes, cudaGetErrorString(err));
+      pds_stft_plan_destroy(plan);
+      return PDS_ERR_CUDA;
+    }
+  }
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(pick_kernel(plan, PDS_F32)),
+                                                plan->fast ? kThreads : kDirectThreads, plan->smem_bytes);
+  plan->grid_limit = prop.multiProcessorCount * std::max(1, occ);
+  *out = plan;
+  return PDS_OK;
+}
+
+extern "C" void pds_stft_plan_destroy(pds_stft_plan* plan) {
+  if (!plan) return;
+  cudaSetDevice(plan->device);
+  if (plan->d_blob) cudaFree(plan->d_blob);
+  if (plan->d_sig) cudaFree(plan->d_sig);
+  if (plan->d_tiles) cudaFree(plan->d_tiles);
+  if (plan->d_out) cudaFree(plan->d_out);
+  delete plan;
+}
+
+extern "C" int pds_stft_num_coeffs(const pds_stft_plan* plan) { return plan ? plan->C : 0; }
+extern "C" int pds_stft_tile_frames(const pds_stft_plan* plan) { return plan ? plan->tile_frames : 0; }
+extern "C" int pds_stft_is_fast_path(const pds_stft_plan* plan) { return plan && plan->fast ? 1 : 0; }
+
+extern "C" int64_t pds_stft_num_frames(const pds_stft_plan* plan, int64_t sig_len) {
+  if (!plan || sig_len < plan->L / 2 + 1) return 0;
+  return (sig_len + plan->S / 2) / plan->S;
+}
+
+extern "C" int pds_stft_layout(const pds_stft_plan* plan, int64_t n_utts, const int64_t* sig_len,
+                               int64_t* frame_off, int64_t* n_tiles) {
+  PDS_REQUIRE(plan && sig_len && frame_off && n_tiles && n_utts >= 0, "bad argument");
+  int64_t rows = 0, tiles = 0;
+  const int64_t tf = plan->tile_frames;
+  for (int64_t u = 0; u < n_utts; ++u) {
+    PDS_REQUIRE(sig_len[u] >= 0 && sig_len[u] < (int64_t)1 << 31, "utterance %lld has length %lld",
+                (long long)u, (long long)sig_len[u]);
+    frame_off[u] = rows;
+    const int64_t t = pds_stft_num_frames(plan, sig_len[u]);
+    rows += t;
+    tiles += (t + tf - 1) / tf;
+  }
+  frame_off[n_utts] = rows;
+  *n_tiles = tiles;
+  return PDS_OK;
+}
+
+extern "C" int pds_stft_fill_tiles(const pds_stft_plan* plan, int64_t n_utts, const int64_t* sig_off,
+                                   const int64_t* sig_len, const int64_t* frame_off, pds_tile* tiles) {
+  PDS_REQUIRE(plan && sig_off && sig_len && frame_off && (tiles || n_utts == 0), "bad argument");
+  const int64_t tf = plan->tile_frames;
+  int64_t n = 0;
+  for (int64_t u = 0; u < n_utts; ++u) {
+    const int64_t t_total = frame_off[u + 1] - frame_off[u];
+    for (int64_t t0 = 0; t0 < t_total; t0 += tf) {
+      pds_tile& tile = tiles[n++];
+      tile.sig_off = sig_off[u];
+      tile.sig_len = (int32_t)sig_len[u];
+      tile.start = (int32_t)(t0 * plan->S - plan->pad_left);
+      tile.nframes = (int32_t)std::min<int64_t>(tf, t_total - t0);
+      tile.utt = (int32_t)u;
+      tile.out_row = frame_off[u] + t0;
+    }
+  }
+  return PDS_OK;
+}
+
+extern "C" int pds_stft_fill_tiles_range(const pds_stft_plan* plan, int64_t sig_off, int64_t buf_len,
+                                         int64_t buf_origin, int64_t first_frame, int64_t nframes,
+                                         int64_t out_row, pds_tile* tiles, int64_t* n_tiles) {
+  PDS_REQUIRE(plan && n_tiles && nframes >= 0 && buf_len >= 0, "bad argument");
+  const int64_t tf = plan->tile_frames;
+  int64_t n = 0;
+  for (int64_t t0 = 0; t0 < nframes; t0 += tf) {
+    if (tiles) {
+      pds_tile& tile = tiles[n];
+      tile.sig_off = sig_off;
+      tile.sig_len = (int32_t)buf_len;
+      tile.start = (int32_t)((first_frame + t0) * plan->S - plan->pad_left - buf_origin);
+      tile.nframes = (int32_t)std::min<int64_t>(tf, nframes - t0);
+      tile.utt = 0;
+      tile.out_row = out_row + t0;
+    }
+    ++n;
+  }
+  *n_tiles = n;
+  return PDS_OK;
+}
+
+extern "C" int pds_stft_run(pds_stft_plan* plan, const void* d_signal, int sig_dtype,
+                            const pds_tile* d_tiles, int64_t n_tiles, float* d_out, uint64_t seed,
+                            void* stream) {
+  PDS_REQUIRE(plan, "null plan");
+  PDS_REQUIRE(sig_dtype == PDS_F32 || sig_dtype == PDS_I16 || sig_dtype == PDS_F64,
+              "unknown sample dtype %d", sig_dtype);
+  if (n_tiles == 0) return PDS_OK;
+  PDS_REQUIRE(d_signal && d_tiles && d_out && n_tiles > 0, "null buffer");
+  StftParams p = plan->params;
+  p.sig = d_signal;
+  p.tiles = d_tiles;
+  p.n_tiles = n_tiles;
+  p.out = d_out;
+  p.seed = seed;
+  KernelFn fn = pick_kernel(plan, sig_dtype);
+  const int grid = (int)std::min<int64_t>(n_tiles, plan->grid_limit);
+  const int threads = plan->fast ? kThreads : kDirectThreads;
+  fn<<<grid, threads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+  PDS_CUDA_CHECK(cudaGetLastError());
+  return PDS_OK;
+}
+
+namespace {
+int ensure(void** ptr, size_t* cap, size_t need) {
+  if (*cap >= need) return PDS_OK;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *cap = 0;
+  PDS_CUDA_CHECK(cudaMalloc(ptr, need));
+  *cap = need;
+  return PDS_OK;
+}
+}  // namespace
+
+extern "C" int pds_stft_compute_host(pds_stft_plan* plan, const void* h_signal, int sig_dtype,
+                                     int64_t total_samples, int64_t n_utts, const int64_t* sig_off,
+                                     const int64_t* sig_len, float* h_out, int64_t out_capacity_rows,
+                                     int64_t* frame_off, uint64_t seed) {
+  PDS_REQUIRE(plan && sig_off && sig_len && frame_off && n_utts >= 0 && total_samples >= 0, "bad argument");
+  PDS_REQUIRE(sig_dtype == PDS_F32 || sig_dtype == PDS_I16 || sig_dtype == PDS_F64,
+              "unknown sample dtype %d", sig_dtype);
+  for (int64_t u = 0; u < n_utts; ++u)
+    PDS_REQUIRE(sig_off[u] >= 0 && sig_off[u] + sig_len[u] <= total_samples,
+                "utterance %lld lies outside the packed buffer", (long long)u);
+  int64_t n_tiles = 0;
+  int rc = pds_stft_layout(plan, n_utts, sig_len, frame_off, &n_tiles);
+  if (rc != PDS_OK) return rc;
+  const int64_t rows = frame_off[n_utts];
+  PDS_REQUIRE(rows <= out_capacity_rows, "output holds %lld rows, need %lld",
+              (long long)out_capacity_rows, (long long)rows);
+  if (rows == 0) return PDS_OK;
+  PDS_REQUIRE(h_signal && h_out, "null buffer");
+  PDS_CUDA_CHECK(cudaSetDevice(plan->device));
+  std::vector<pds_tile> tiles((size_t)n_tiles);
+  rc = pds_stft_fill_tiles(plan, n_utts, sig_off, sig_len, frame_off, tiles.data());
+  if (rc != PDS_OK) return rc;
+  size_t tiles_bytes = plan->d_tiles_cap * sizeof(pds_tile);
+  rc = ensure(&plan->d_sig, &plan->d_sig_bytes, (size_t)total_samples * dtype_size(sig_dtype) + 16);
+  if (rc == PDS_OK) {
+    void* t = plan->d_tiles;
+    rc = ensure(&t, &tiles_bytes, (size_t)n_tiles * sizeof(pds_tile));
+    plan->d_tiles = static_cast<pds_tile*>(t);
+    plan->d_tiles_cap = tiles_bytes / sizeof(pds_tile);
+  }
+  if (rc == PDS_OK) {
+    void* o = plan->d_out;
+    rc = ensure(&o, &plan->d_out_bytes, (size_t)rows * plan->C * sizeof(float));
+    plan->d_out = static_cast<float*>(o);
+  }
+  if (rc != PDS_OK) return rc;
+  PDS_CUDA_CHECK(cudaMemcpyAsync(plan->d_sig, h_signal, (size_t)total_samples * dtype_size(sig_dtype),
+                                 cudaMemcpyHostToDevice, 0));
+  PDS_CUDA_CHECK(cudaMemcpyAsync(plan->d_tiles, tiles.data(), (size_t)n_tiles * sizeof(pds_tile),
+                                 cudaMemcpyHostToDevice, 0));
+  rc = pds_stft_run(plan, plan->d_sig, sig_dtype, plan->d_tiles, n_tiles, plan->d_out, seed, nullptr);
+  if (rc != PDS_OK) return rc;
+  PDS_CUDA_CHECK(cudaMemcpyAsync(h_out, plan->d_out, (size_t)rows * plan->C * sizeof(float),
+                                 cudaMemcpyDeviceToHost, 0));
+  PDS_CUDA_CHECK(cudaStreamSynchronize(0));
+  return PDS_OK;
+}
