@@ -34,6 +34,7 @@ __all__ = [
     "frame_by_frame_calculation",
     "FrameComputer",
     "LinearFilterBankFrameComputer",
+    "BatchLayout",
     "PackedSignals",
     "ShortIntegrationFrameComputer",
     "ShortTimeFourierTransformFrameComputer",
@@ -332,16 +333,64 @@ class ShortTimeFourierTransformFrameComputer(LinearFilterBankFrameComputer):
         self._plans[key] = plan
         return plan
 
-    def compute_packed_device(
-        self,
-        d_signal,
-        offsets: np.ndarray,
-        lengths: np.ndarray,
-        preemph: float = 0.0,
-        dither: float = 0.0,
-        dither_first: bool = True,
-        seed: int = 0,
-    ):
+    def plan_batch(self, offsets: np.ndarray, lengths: np.ndarray, device=None, utt_base: int = 0) -> "BatchLayout":
+        """Work list for a packed batch: frame offsets on the host, tile table in HBM
+
+        The layout depends only on the utterance offsets / lengths, so it can be built once and
+        reused for every batch with the same packing (``utt_base`` is added to the utterance ids
+        that key the dither stream, e.g. the global index of the shard's first utterance).
+        """
+        import ctypes
+
+        import torch
+
+        from ._gpu import TILE_DTYPE, current_device
+        from ._lib import check, get_lib
+
+        lib = get_lib()
+        device = current_device() if device is None else device
+        plan = self._plan(device)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        n_utts = len(lengths)
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        frame_off = np.zeros(n_utts + 1, dtype=np.int64)
+        n_tiles = ctypes.c_int64(0)
+        check(lib.pds_stft_layout(plan.handle, n_utts, lengths.ctypes.data_as(i64p),
+                                  frame_off.ctypes.data_as(i64p), ctypes.byref(n_tiles)))
+        tiles = np.empty(n_tiles.value, dtype=TILE_DTYPE)
+        if n_tiles.value:
+            check(lib.pds_stft_fill_tiles(plan.handle, n_utts, offsets.ctypes.data_as(i64p),
+                                          lengths.ctypes.data_as(i64p), frame_off.ctypes.data_as(i64p),
+                                          tiles.ctypes.data))
+            if utt_base:
+                tiles["utt"] += utt_base
+        d_tiles = torch.from_numpy(tiles.view(np.uint8)).to(device, non_blocking=True)
+        return BatchLayout(frame_off, d_tiles, int(n_tiles.value), self.num_coeffs, device)
+
+    def run_batch(self, layout: "BatchLayout", d_signal, out=None, preemph: float = 0.0,
+                  dither: float = 0.0, dither_first: bool = True, seed: int = 0):
+        """Enqueue the fused kernel for a planned batch on the current stream; no host sync"""
+        import torch
+
+        from ._gpu import stream_ptr
+        from ._lib import check, get_lib
+
+        device = d_signal.device
+        code = {torch.float32: 0, torch.int16: 1, torch.float64: 2}.get(d_signal.dtype)
+        if code is None:
+            raise ValueError(f"unsupported sample dtype {d_signal.dtype}")
+        plan = self._plan(device, preemph, dither, dither_first)
+        if out is None:
+            out = torch.empty((layout.rows, self.num_coeffs), dtype=torch.float32, device=device)
+        if layout.n_tiles:
+            with torch.cuda.device(device):
+                check(get_lib().pds_stft_run(plan.handle, d_signal.data_ptr(), code,
+                                             layout.d_tiles.data_ptr(), layout.n_tiles, out.data_ptr(),
+                                             int(seed) & (2 ** 64 - 1), stream_ptr(device)))
+        return out
+
+    def compute_packed_device(self, d_signal, offsets: np.ndarray, lengths: np.ndarray, **pre):
         """Run the fused kernel on a packed batch that is already resident in HBM
 
         Parameters
@@ -350,6 +399,8 @@ class ShortTimeFourierTransformFrameComputer(LinearFilterBankFrameComputer):
             1D CUDA tensor (float32, int16 or float64) holding all utterances
         offsets, lengths : np.ndarray
             int64 host arrays: start and length of each utterance inside `d_signal`
+        **pre
+            ``preemph``, ``dither``, ``dither_first``, ``seed``: pre-processing fused into the load
 
         Returns
         -------
@@ -359,43 +410,8 @@ class ShortTimeFourierTransformFrameComputer(LinearFilterBankFrameComputer):
         frame_off : np.ndarray
             int64, length ``len(lengths) + 1``
         """
-        import ctypes
-
-        import torch
-
-        from ._gpu import TILE_DTYPE, dtype_code, stream_ptr
-        from ._lib import check, get_lib
-
-        lib = get_lib()
-        device = d_signal.device
-        code = {torch.float32: 0, torch.int16: 1, torch.float64: 2}.get(d_signal.dtype)
-        if code is None:
-            raise ValueError(f"unsupported sample dtype {d_signal.dtype}")
-        plan = self._plan(device, preemph, dither, dither_first)
-        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
-        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
-        n_utts = len(lengths)
-        i64p = ctypes.POINTER(ctypes.c_int64)
-        frame_off = np.zeros(n_utts + 1, dtype=np.int64)
-        n_tiles = ctypes.c_int64(0)
-        check(lib.pds_stft_layout(plan.handle, n_utts, lengths.ctypes.data_as(i64p),
-                                  frame_off.ctypes.data_as(i64p), ctypes.byref(n_tiles)))
-        rows = int(frame_off[-1])
-        feats = torch.empty((rows, self.num_coeffs), dtype=torch.float32, device=device)
-        if rows == 0:
-            return feats, frame_off
-        tiles = np.empty(n_tiles.value, dtype=TILE_DTYPE)
-        check(lib.pds_stft_fill_tiles(plan.handle, n_utts, offsets.ctypes.data_as(i64p),
-                                      lengths.ctypes.data_as(i64p), frame_off.ctypes.data_as(i64p),
-                                      tiles.ctypes.data))
-        d_tiles = torch.from_numpy(tiles.view(np.uint8)).to(device, non_blocking=True)
-        with torch.cuda.device(device):
-            check(lib.pds_stft_run(plan.handle, d_signal.data_ptr(), code, d_tiles.data_ptr(),
-                                   n_tiles.value, feats.data_ptr(), int(seed) & (2 ** 64 - 1),
-                                   stream_ptr(device)))
-        # keep the tile table alive until the kernel has consumed it
-        d_tiles.record_stream(torch.cuda.current_stream(device))
-        return feats, frame_off
+        layout = self.plan_batch(offsets, lengths, d_signal.device)
+        return self.run_batch(layout, d_signal, **pre), layout.frame_off
 
     def compute_batch(self, signals: Union[PackedSignals, Sequence[np.ndarray]], **pre) -> List[np.ndarray]:
         """Features of many signals with one launch; returns one float32 array per signal"""
@@ -801,6 +817,21 @@ class ShortIntegrationFrameComputer(LinearFilterBankFrameComputer):
 
 
 SIFrameComputer = ShortIntegrationFrameComputer
+
+
+class BatchLayout:
+    """Result of ``plan_batch``: where each utterance's frames go and the device tile table"""
+
+    def __init__(self, frame_off, d_tiles, n_tiles, num_coeffs, device):
+        self.frame_off = frame_off
+        self.d_tiles = d_tiles
+        self.n_tiles = n_tiles
+        self.num_coeffs = num_coeffs
+        self.device = device
+
+    @property
+    def rows(self) -> int:
+        return int(self.frame_off[-1])
 
 
 class _PlanHandle:

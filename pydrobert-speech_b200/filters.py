@@ -54,9 +54,9 @@ def _half_width(width: int) -> int:
 def _check_hz_range(low_hz, high_hz, sampling_rate):
     # shared by fbank / gabor / gammatone (filters.py:488-493, 702-707, 983-988)
     if low_hz < 0 or (high_hz and (high_hz <= low_hz or high_hz > sampling_rate // 2)):
-        raise ValueError(
-            "Invalid frequency range: ({:.2f},{:.2f}".format(low_hz, high_hz)
-        )
+        # (the reference formats high_hz=None here and dies with a TypeError instead)
+        top = float("nan") if high_hz is None else high_hz
+        raise ValueError("Invalid frequency range: ({:.2f},{:.2f}".format(low_hz, top))
 
 
 def _uniform_scale_points(scaling_function, low_hz, high_hz, num_filts, half_step):

@@ -1,0 +1,229 @@
+"""Corpus-scale driver: pre-processors + frame computer + post-processors over packed batches.
+
+This is the batched counterpart of the reference's per-utterance loop in
+``signals-to-torch-feat-dir`` (``command_line.py:102-136, 585-606``): utterances are packed into
+length-bucketed chunks, each chunk is copied host->device from pinned memory on a copy stream
+while the previous chunk is in the fused kernel and the one before that is being copied back
+(three CUDA streams, double-buffered device memory), so the end-to-end rate approaches the slower
+of PCIe and the kernels.
+
+Fusion rules: ``Dither`` and ``Preemphasize`` (each at most once) in front of an STFT computer are
+folded into the kernel's sample staging; ``Deltas`` along time and a trailing ``Standardize`` with
+global statistics run as device passes on the resident features.  Anything else falls back to the
+processors' own ``apply`` on the host arrays, after the device part.
+"""
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .compute import (
+    FrameComputer,
+    PackedSignals,
+    ShortIntegrationFrameComputer,
+    ShortTimeFourierTransformFrameComputer,
+)
+from .post import Deltas, PostProcessor, Standardize
+from .pre import Dither, PreProcessor, Preemphasize
+
+__all__ = ["FeaturePipeline", "shard_utterances"]
+
+
+def shard_utterances(lengths: Sequence[int], world_size: int) -> List[np.ndarray]:
+    """Deal utterances to ranks so that every rank gets about the same number of samples
+
+    Longest first, each to the currently lightest rank (greedy LPT).  Utterances are the unit of
+    sharding: they are independent, so no rank ever needs another rank's samples.
+    Returns, per rank, the sorted indices of its utterances.
+    """
+    lengths = np.asarray(lengths, dtype=np.int64)
+    order = np.argsort(-lengths, kind="stable")
+    loads = np.zeros(world_size, dtype=np.int64)
+    shards: List[List[int]] = [[] for _ in range(world_size)]
+    for idx in order:
+        rank = int(np.argmin(loads))
+        shards[rank].append(int(idx))
+        loads[rank] += lengths[idx]
+    return [np.array(sorted(s), dtype=np.int64) for s in shards]
+
+
+class FeaturePipeline:
+    """``preprocessors -> computer -> postprocessors`` over whole batches on one GPU"""
+
+    def __init__(
+        self,
+        computer: FrameComputer,
+        preprocessors: Sequence[PreProcessor] = (),
+        postprocessors: Sequence[PostProcessor] = (),
+        seed: int = 0,
+        chunk_samples: int = 1 << 26,
+        post_along_time: bool = True,
+    ):
+        """
+        Parameters
+        ----------
+        post_along_time
+            If True (API use), ``Deltas`` filter along the time axis and run on the device.  If
+            False (the reference CLI's behaviour), every post-processor is applied
+            per utterance through its own ``apply(features)`` with the default ``axis=-1``.
+        """
+        self.computer = computer
+        self.seed = int(seed)
+        self.chunk_samples = int(chunk_samples)
+        self._post_along_time = bool(post_along_time)
+        self._fused_pre = dict(preemph=0.0, dither=0.0, dither_first=True)
+        self._host_pre: List[PreProcessor] = []
+        self._device_post: List[PostProcessor] = []
+        self._host_post: List[PostProcessor] = []
+        self._classify(list(preprocessors), list(postprocessors))
+
+    def _classify(self, pre, post):
+        kinds = [type(p) for p in pre]
+        fusable = (
+            isinstance(self.computer, ShortTimeFourierTransformFrameComputer)
+            and all(k in (Dither, Preemphasize) for k in kinds)
+            and kinds.count(Dither) <= 1
+            and kinds.count(Preemphasize) <= 1
+        )
+        if fusable:
+            for p in pre:
+                if isinstance(p, Dither):
+                    self._fused_pre["dither"] = float(p.coeff)
+                else:
+                    self._fused_pre["preemph"] = float(p.coeff)
+            if kinds:
+                self._fused_pre["dither_first"] = kinds[0] is Dither
+        else:
+            self._host_pre = pre
+        device_ok = True
+        for p in post:
+            on_device = (
+                isinstance(p, Deltas) and p.concatenate and p._target_axis in (-1, 1) and p._pad_mode == "edge"
+            ) or (isinstance(p, Standardize) and p.have_stats)
+            if device_ok and on_device and self._post_along_time:
+                self._device_post.append(p)
+            else:
+                device_ok = False
+                self._host_post.append(p)
+
+    @property
+    def num_coeffs(self) -> int:
+        n = self.computer.num_coeffs
+        for p in self._device_post:
+            if isinstance(p, Deltas):
+                n *= p.num_deltas + 1
+        return n
+
+    # ---- device-resident -----------------------------------------------------------------
+    def run_device(self, d_signal, offsets, lengths, utt_base: int = 0):
+        """Packed CUDA signal in -> ``(rows, num_coeffs)`` CUDA features + host row offsets"""
+        import torch
+
+        computer = self.computer
+        if isinstance(computer, ShortTimeFourierTransformFrameComputer):
+            layout = computer.plan_batch(offsets, lengths, d_signal.device, utt_base)
+            feats = computer.run_batch(layout, d_signal, seed=self.seed, **self._fused_pre)
+            frame_off = layout.frame_off
+        else:
+            feats, frame_off = computer.compute_packed_device(d_signal, offsets, lengths)
+        if self._device_post and feats.shape[0]:
+            row_off = None
+            for p in self._device_post:
+                if isinstance(p, Deltas):
+                    if row_off is None:
+                        row_off = torch.from_numpy(frame_off).to(feats.device)
+                    feats = p.apply_device(feats, row_off)
+                else:
+                    feats = p.apply_device(feats, out=feats)
+        return feats, frame_off
+
+    # ---- host in, host out, pipelined ----------------------------------------------------
+    def _chunks(self, lengths: np.ndarray) -> List[Tuple[int, int]]:
+        bounds, begin, acc = [], 0, 0
+        for u, n in enumerate(lengths):
+            if acc and acc + n > self.chunk_samples:
+                bounds.append((begin, u))
+                begin, acc = u, 0
+            acc += int(n)
+        if begin < len(lengths) or not bounds:
+            bounds.append((begin, len(lengths)))
+        return bounds
+
+    def run_host(self, packed: PackedSignals, out: Optional[np.ndarray] = None, device=None,
+                 utt_base: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        """Features of a packed host batch; returns ``(feats, frame_off)`` on the host
+
+        ``packed.data`` (and ``out`` if given) should live in pinned memory for the copies to
+        overlap with the kernels.  Utterances are processed in chunks of about ``chunk_samples``
+        samples, three streams deep.
+        """
+        import torch
+
+        from ._gpu import current_device
+
+        device = current_device() if device is None else device
+        if self._host_pre or self._host_post:
+            raise NotImplementedError(
+                "run_host covers the device-resident part only; call the pipeline object for chains "
+                "with host-side processors"
+            )
+        counts = np.array([self.computer.num_frames(int(n)) for n in packed.lengths], dtype=np.int64)
+        frame_off = np.zeros(len(counts) + 1, dtype=np.int64)
+        np.cumsum(counts, out=frame_off[1:])
+        width = self.num_coeffs
+        if out is None:
+            out = np.empty((int(frame_off[-1]), width), dtype=np.float32)
+        host_in = torch.from_numpy(packed.data)
+        host_out = torch.from_numpy(out)
+        copy_in, copy_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        compute = torch.cuda.current_stream(device)
+        in_flight = []  # keep device buffers of the last chunks alive
+        for begin, end in self._chunks(packed.lengths):
+            first = int(packed.offsets[begin]) // 4 * 4
+            last = int(packed.offsets[end - 1] + packed.lengths[end - 1]) if end > begin else first
+            with torch.cuda.stream(copy_in):
+                d_sig = host_in[first:last].to(device, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_in)
+            compute.wait_event(ready)
+            feats, _ = self.run_device(d_sig, packed.offsets[begin:end] - first,
+                                       packed.lengths[begin:end], utt_base + begin)
+            d_sig.record_stream(compute)
+            done = torch.cuda.Event()
+            done.record(compute)
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(done)
+                host_out[int(frame_off[begin]) : int(frame_off[end])].copy_(feats, non_blocking=True)
+                feats.record_stream(copy_out)
+            in_flight.append((d_sig, feats))
+            if len(in_flight) > 3:
+                in_flight.pop(0)
+        copy_out.synchronize()
+        compute.synchronize()
+        return out, frame_off
+
+    def __call__(self, signals: Sequence[np.ndarray]) -> List[np.ndarray]:
+        """List of 1-D arrays in, list of ``(T, C)`` float32 arrays out (host post-processors,
+        if any, are applied per utterance and may change ``T`` or ``C``)"""
+        signals = [np.asarray(s) for s in signals]
+        is_stft = isinstance(self.computer, ShortTimeFourierTransformFrameComputer)
+        if self._host_pre:
+            signals = [self._apply_host_pre(s.astype(np.float64)) for s in signals]
+        all_pcm = bool(signals) and all(s.dtype == np.int16 for s in signals)
+        dtype = np.int16 if (all_pcm and is_stft) else np.float32
+        lead = self.computer.pad_left % 4 if is_stft else 0
+        packed = PackedSignals.pack(signals, dtype, lead)
+        saved, self._host_pre = self._host_pre, []
+        try:
+            feats, frame_off = self.run_host(packed)
+        finally:
+            self._host_pre = saved
+        per_utt = [feats[frame_off[u] : frame_off[u + 1]] for u in range(len(signals))]
+        for p in self._host_post:
+            per_utt = [p.apply(f) if len(f) else f for f in per_utt]
+        return per_utt
+
+    def _apply_host_pre(self, signal):
+        for p in self._host_pre:
+            signal = p.apply(signal)
+        return signal

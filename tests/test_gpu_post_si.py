@@ -1,0 +1,196 @@
+"""Parity of the post-processing, pre-processing and short-integration kernels (through the C
+ABI) against the oracle and the goldens produced by the real reference."""
+import warnings
+
+import numpy as np
+import pytest
+
+import cases
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def build(speech, base, cfg):
+    return speech.alias_factory_subclass_from_arg(base, cfg)
+
+
+# ---- Deltas ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("order", (1, 2, 3))
+@pytest.mark.parametrize("ctx", (1, 2, 3))
+def test_deltas_match_reference(speech, golden, order, ctx):
+    data = golden("post")
+    got = speech.post.Deltas(order, context_window=ctx).apply(data["feats"], axis=0)
+    want = data[f"deltas_o{order}_w{ctx}"]
+    assert got.shape == want.shape and got.dtype == data["feats"].dtype
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_deltas_short_and_axes(speech, golden):
+    data = golden("post")
+    got = speech.post.Deltas(2).apply(data["feats"][:3], axis=0)
+    assert np.abs(got - data["deltas_short"]).max() <= 1e-5
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((6, 40, 5))
+    # filter along axis 1, stack on a new leading axis: compare with the oracle slice by slice
+    got = speech.post.Deltas(1, target_axis=0, concatenate=False).apply(x, axis=1)
+    assert got.shape == (2, 6, 40, 5)
+    for i in range(6):
+        want = oracle.deltas(x[i], 1)[:, 5:]
+        assert np.abs(got[1, i] - want).max() <= 1e-5
+    # the reference CLI's default: axis=-1
+    feats = rng.standard_normal((30, 8))
+    got = speech.post.Deltas(2).apply(feats)
+    want = oracle.deltas(feats.T, 2)  # filter along coefficients
+    assert got.shape == (30, 24)
+    assert np.abs(got[:, 8:16] - want[:, 30:60].T).max() <= 1e-5
+
+
+def test_deltas_respect_utterance_boundaries(speech):
+    import torch
+
+    rng = np.random.default_rng(1)
+    lens = [5, 0, 1, 70, 33]
+    feats = rng.standard_normal((sum(lens), 41)).astype(np.float32)
+    row_off = torch.tensor(np.cumsum([0] + lens), dtype=torch.int64, device="cuda")
+    got = speech.post.Deltas(2).apply_device(torch.from_numpy(feats).cuda(), row_off).cpu().numpy()
+    begin = 0
+    for n in lens:
+        if n:
+            want = oracle.deltas(feats[begin : begin + n], 2)
+            assert np.abs(got[begin : begin + n] - want).max() <= 1e-5
+        begin += n
+
+
+# ---- Standardize ------------------------------------------------------------------------------
+def test_cmvn_matches_reference(speech, golden):
+    data = golden("post")
+    std = speech.post.Standardize()
+    begin = 0
+    for n in data["cmvn_chunk_lens"]:
+        std.accumulate(data["cmvn_chunks"][begin : begin + n])
+        begin += n
+    assert np.allclose(std.stats, data["cmvn_stats"], rtol=1e-12)  # float64 accumulation, exact inputs
+    first = data["cmvn_chunks"][: data["cmvn_chunk_lens"][0]]
+    got = std.apply(first)
+    assert got.dtype == np.float64
+    assert np.abs(got - data["cmvn_applied"]).max() <= 1e-5
+    feats = data["feats"]
+    assert np.abs(speech.post.Standardize().apply(feats) - data["cmvn_local"]).max() <= 1e-5
+    assert np.abs(speech.post.Standardize(norm_var=False).apply(feats) - data["cmvn_applied_novar"]).max() <= 1e-5
+
+
+def test_cmvn_errors_and_io(speech, tmp_path):
+    std = speech.post.Standardize()
+    with pytest.raises(ValueError, match="empty"):
+        std.accumulate(np.zeros((0, 3)))
+    with pytest.raises(ValueError, match="global statistics"):
+        std.apply(np.ones(4))
+    rng = np.random.default_rng(2)
+    std.accumulate(rng.standard_normal((100, 4)), axis=1)
+    with pytest.raises(ValueError, match="Expected feature vector of length 4; got 5"):
+        std.accumulate(np.ones((3, 5)))
+    for name in ("stats.npy", "stats.npz", "stats.bin"):
+        path = str(tmp_path / name)
+        std.save(path)
+        loaded = speech.post.Standardize(path)
+        assert np.allclose(loaded.stats, std.stats)
+    const = np.ones((10, 3))
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        out = speech.post.Standardize().apply(const)
+    assert any("0 variance" in str(w.message) for w in caught)
+    assert np.allclose(out, 0)
+
+
+def test_cmvn_large_matches_float64(speech):
+    import torch
+
+    rng = np.random.default_rng(3)
+    feats = (rng.standard_normal((200003, 123)) * 7 + 3).astype(np.float32)
+    std = speech.post.Standardize()
+    std.accumulate_device(torch.from_numpy(feats).cuda())
+    want = oracle.cmvn_accumulate(feats)
+    assert np.allclose(std.stats, want, rtol=1e-12)
+    got = std.apply_device(torch.from_numpy(feats).cuda()).cpu().numpy()
+    assert np.abs(got - oracle.cmvn_apply(feats, want)).max() <= 2e-5
+    assert abs(got.mean()) < 1e-4 and abs(got.std() - 1) < 1e-3
+
+
+# ---- pre-processors ---------------------------------------------------------------------------
+def test_preemphasis_kernel(speech, golden):
+    data = golden("stft")
+    got = speech.pre.Preemphasize(0.97).apply(data["preemph/signal"].astype(np.float64))
+    assert got.dtype == np.float64
+    want = data["preemph/signal_out"]
+    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+    two_d = np.stack([data["preemph/signal"][:100], data["preemph/signal"][100:200]])
+    with pytest.warns(DeprecationWarning):
+        got = speech.pre.Preemphasize(0.5).apply(two_d, axis=1)
+    assert np.allclose(got[1], oracle.preemphasize(two_d[1], 0.5), rtol=1e-5, atol=1e-3)
+
+
+def test_dither_kernel_statistics(speech):
+    # reference tests/test_pre.py:32-38
+    np.random.seed(1)
+    signal = np.zeros(200000)
+    out = speech.pre.Dither(2.0).apply(signal)
+    assert abs(out.std() - 2.0) < 1e-2 and abs(out.mean()) < 2e-2
+    assert np.all(signal == 0)  # not in place
+    np.random.seed(1)
+    assert np.array_equal(out, speech.pre.Dither(2.0).apply(signal))
+
+
+# ---- short integration ------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(cases.SI_CASES))
+def test_si_matches_reference(speech, golden, name):
+    cfg, _ = cases.SI_CASES[name]
+    data = golden("si")
+    computer = build(speech, speech.compute.FrameComputer, cfg)
+    signal = data[name + "/signal"]
+    want = data[name + "/feats"]
+    got = computer.compute_full(signal)
+    assert got.shape == want.shape and got.dtype == signal.dtype
+    if cfg.get("use_log", True):
+        assert np.abs(got - want).max() <= 1e-3
+        lin = build(speech, speech.compute.FrameComputer, dict(cfg, use_log=False))
+        lin_got, lin_want = lin.compute_full(signal).astype(np.float64), data[name + "/feats_linear"]
+    else:
+        lin_got, lin_want = got.astype(np.float64), want
+    scale = np.maximum(np.abs(lin_want), 1e-6 * np.abs(lin_want).max(axis=1, keepdims=True))
+    assert (np.abs(lin_got - lin_want) / scale).max() <= 1e-4
+
+
+def test_si_chunked_and_batch(speech):
+    rng = np.random.default_rng(4)
+    computer = build(speech, speech.compute.FrameComputer, cases.SI_CASES["si_gabor41"][0])
+    for n in (0, 1, 256, 1024, 3000):
+        sig = rng.standard_normal(n)
+        full = computer.compute_full(sig)
+        chunked = speech.compute.frame_by_frame_calculation(computer, sig, chunk_size=333)
+        assert chunked.shape == full.shape == (computer.num_frames(n), 41)
+        assert np.allclose(full, chunked, atol=1e-5)
+    sigs = [rng.standard_normal(n).astype(np.float32) for n in (2000, 0, 50, 4321)]
+    for sig, feats in zip(sigs, computer.compute_batch(sigs)):
+        assert np.array_equal(feats, computer.compute_full(sig))
+    with pytest.raises(ValueError, match="float type"):
+        computer.compute_full(np.zeros(100, dtype=np.int16))
+
+
+# ---- pipeline ---------------------------------------------------------------------------------
+def test_pipeline_matches_step_by_step(speech):
+    from pydrobert_speech_b200.pipeline import FeaturePipeline
+
+    rng = np.random.default_rng(5)
+    computer = build(speech, speech.compute.FrameComputer, cases.README_FBANK)
+    sigs = [(rng.standard_normal(n) * 1000).astype(np.float32) for n in (16000, 300, 0, 52000, 8000)]
+    pipe = FeaturePipeline(computer, [speech.pre.Preemphasize(0.97)], [speech.post.Deltas(2)], chunk_samples=20000)
+    out = pipe(sigs)
+    for sig, feats in zip(sigs, out):
+        base = oracle.stft_features(
+            oracle.preemphasize(sig, 0.97), computer._window, 512, computer._filt_start_idxs,
+            computer._truncated_filts, 160, 199, True, True, True, True)
+        want = oracle.deltas(base, 2) if len(base) else np.zeros((0, 123))
+        assert feats.shape == want.shape
+        if len(want):
+            assert np.abs(feats - want).max() <= 1e-3

