@@ -1,11 +1,7 @@
 #!/bin/bash
-# GPU session: parity tests, smoke, a short bench, launch list + full ncu capture of the top kernel
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1
+timeout 600 python -m pytest tests -x -q -m gpu --durations=8 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -25 gpurun_out/pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-python tools/probe_stft.py 2000 > gpurun_out/probe.log 2>&1; tail -4 gpurun_out/probe.log
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+tail -22 gpurun_out/pytest_gpu.log
+timeout 300 python tools/probe_stft.py 2000 > gpurun_out/probe.log 2>&1; tail -4 gpurun_out/probe.log

@@ -35,7 +35,7 @@ typedef enum pds_status {
 typedef enum pds_dtype {
   PDS_F32 = 0, /* IEEE float32 samples                                   */
   PDS_I16 = 1, /* signed 16-bit PCM samples (converted to float, unscaled) */
-  PDS_F64 = 2  /* IEEE float64 samples (rounded to float32 on load)        */
+  PDS_F64 = 2  /* reserved: the kernels take float32 / int16; hosts convert float64 first */
 } pds_dtype;
 
 const char* pds_last_error(void);

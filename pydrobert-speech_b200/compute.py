@@ -377,7 +377,9 @@ class ShortTimeFourierTransformFrameComputer(LinearFilterBankFrameComputer):
         from ._lib import check, get_lib
 
         device = d_signal.device
-        code = {torch.float32: 0, torch.int16: 1, torch.float64: 2}.get(d_signal.dtype)
+        if d_signal.dtype == torch.float64:
+            d_signal = d_signal.float()  # the kernels compute in float32 anyway
+        code = {torch.float32: 0, torch.int16: 1}.get(d_signal.dtype)
         if code is None:
             raise ValueError(f"unsupported sample dtype {d_signal.dtype}")
         plan = self._plan(device, preemph, dither, dither_first)

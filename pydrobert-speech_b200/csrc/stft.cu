@@ -4,9 +4,12 @@
 // frames of one utterance.  Per tile:
 //
 //   stage   : the contiguous span of samples the tile touches ((nframes-1)*S + L floats) is
-//             copied once from HBM to shared memory (128-bit loads when the span is interior
-//             and aligned), with symmetric reflection at the utterance edges and, optionally,
-//             dither and pre-emphasis applied on the way (pre.py:90-149).
+//             copied once from HBM to shared memory.  Interior, 16-byte aligned float32 spans
+//             are fetched by ONE thread with a TMA bulk copy (cp.async.bulk + mbarrier) that is
+//             issued as soon as the previous tile's fft phase has released the buffer, so the
+//             copy overlaps that tile's bank and store phases.  Utterance edges (symmetric
+//             reflection), int16 input and fused dither / pre-emphasis (pre.py:90-149) take a
+//             cooperative per-element path.
 //   fft     : sub-groups of G lanes each take a frame: window multiply, raw-frame energy,
 //             R1-point in-register DFT, twiddle, one shared-memory exchange, G-point DFT(s),
 //             real-FFT split through warp shuffles, |X|^2 (or |X|) -> s_P[bin][frame].
@@ -74,32 +77,55 @@ __device__ __forceinline__ float preprocessed_sample(const T* __restrict__ sig, 
   return x;
 }
 
-template <typename T, int THREADS>
-__device__ __forceinline__ void stage_samples(float* __restrict__ s_x, const StftParams& p,
-                                              const pds_tile& tile, int span) {
-  const T* __restrict__ sig = static_cast<const T*>(p.sig);
-  const int tid = threadIdx.x;
+// ---- mbarrier / TMA bulk copy helpers (sm_90+ PTX) ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(ptr));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred done;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n"
+      "@done bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Can this tile's span be fetched by a single TMA bulk copy?  (uniform across the CTA)
+template <typename T>
+__device__ __forceinline__ bool tile_is_bulk(const StftParams& p, const pds_tile& tile, int span) {
+  if (sizeof(T) != 4 || p.dither != 0.f || p.preemph != 0.f) return false;
   const long long first = tile.start;
-  const bool interior = first >= 0 && first + span <= (long long)tile.sig_len;
-  const bool plain = p.dither == 0.f && p.preemph == 0.f;
-  if (sizeof(T) == 4 && interior && plain &&
-      ((reinterpret_cast<uintptr_t>(sig + tile.sig_off + first) & 15u) == 0)) {
-    // interior + aligned: straight 128-bit copy, read-only path, no L1 allocation
-    const float4* __restrict__ src = reinterpret_cast<const float4*>(sig + tile.sig_off + first);
-    float4* dst = reinterpret_cast<float4*>(s_x);
-    const int n4 = span >> 2;
-    for (int i = tid; i < n4; i += THREADS) {
-      float4 v;
-      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                   : "l"(src + i));
-      dst[i] = v;
-    }
-    for (int i = (n4 << 2) + tid; i < span; i += THREADS)
-      s_x[i] = load_sample(sig, tile.sig_off + first + i);
-    return;
-  }
-  for (int i = tid; i < span; i += THREADS) {
+  if (first < 0 || first + span > (long long)tile.sig_len || (span & 3)) return false;
+  const T* src = static_cast<const T*>(p.sig) + tile.sig_off + first;
+  return (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+}
+
+// Cooperative per-element staging: reflection at the edges, dtype conversion, fused pre-processing
+template <typename T, int THREADS>
+__device__ __forceinline__ void stage_samples_slow(float* __restrict__ s_x, const StftParams& p,
+                                                   const pds_tile& tile, int span) {
+  const T* __restrict__ sig = static_cast<const T*>(p.sig);
+  const long long first = tile.start;
+  for (int i = threadIdx.x; i < span; i += THREADS) {
     const long long g = reflect_index(first + i, tile.sig_len);
     s_x[i] = preprocessed_sample(sig, tile.sig_off, g, p, tile.utt);
   }
@@ -123,16 +149,30 @@ __device__ __forceinline__ void bank_phase(const float* __restrict__ s_P,
     const float4* __restrict__ wt = reinterpret_cast<const float4*>(weights + s_off[f]);
     const float* __restrict__ pp = s_P + s_lo[f] * STRIDE + lane;
     const int n4 = s_n4[f];
-    float acc0 = 0.f, acc1 = 0.f;
-    for (int j = 0; j < n4; ++j) {
-      const float4 w = wt[j];
-      acc0 = fmaf(pp[0], w.x, acc0);
-      acc1 = fmaf(pp[STRIDE], w.y, acc1);
-      acc0 = fmaf(pp[2 * STRIDE], w.z, acc0);
-      acc1 = fmaf(pp[3 * STRIDE], w.w, acc1);
-      pp += 4 * STRIDE;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    int j = 0;
+    for (; j + 1 < n4; j += 2) {  // eight taps per trip, loads first: four independent chains
+      const float4 wa = wt[j], wb = wt[j + 1];
+      const float p0 = pp[0], p1 = pp[STRIDE], p2 = pp[2 * STRIDE], p3 = pp[3 * STRIDE];
+      const float p4 = pp[4 * STRIDE], p5 = pp[5 * STRIDE], p6 = pp[6 * STRIDE], p7 = pp[7 * STRIDE];
+      acc0 = fmaf(p0, wa.x, acc0);
+      acc1 = fmaf(p1, wa.y, acc1);
+      acc2 = fmaf(p2, wa.z, acc2);
+      acc3 = fmaf(p3, wa.w, acc3);
+      acc0 = fmaf(p4, wb.x, acc0);
+      acc1 = fmaf(p5, wb.y, acc1);
+      acc2 = fmaf(p6, wb.z, acc2);
+      acc3 = fmaf(p7, wb.w, acc3);
+      pp += 8 * STRIDE;
     }
-    float v = acc0 + acc1;
+    if (j < n4) {
+      const float4 wa = wt[j];
+      acc0 = fmaf(pp[0], wa.x, acc0);
+      acc1 = fmaf(pp[STRIDE], wa.y, acc1);
+      acc2 = fmaf(pp[2 * STRIDE], wa.z, acc2);
+      acc3 = fmaf(pp[3 * STRIDE], wa.w, acc3);
+    }
+    float v = (acc0 + acc1) + (acc2 + acc3);
     if (p.use_log) v = __logf(fmaxf(v, p.log_floor));
     s_out[lane * p.C + e_off + f] = v;
   }
@@ -146,7 +186,7 @@ __device__ __forceinline__ void bank_phase(const float* __restrict__ s_P,
 
 // shared-memory carve-up shared by host (size computation) and device
 struct SmemLayout {
-  int x, w, scr, P, e, lo, n4, off, wt, total;  // offsets in floats; total in bytes
+  int x, w, scr, P, e, out, bar, lo, n4, off, wt, total;  // offsets in floats; total in bytes
 };
 
 __host__ __device__ inline int take_floats(int& cursor, int n) {
@@ -155,16 +195,19 @@ __host__ __device__ inline int take_floats(int& cursor, int n) {
   return at;
 }
 
-__host__ __device__ inline SmemLayout fused_layout(int N, int G, int R1, int span_max, int F,
+__host__ __device__ inline SmemLayout fused_layout(int N, int G, int R1, int span_max, int F, int C,
                                                    int weights_floats) {
   SmemLayout s;
   const int K = N / 2 + 1;
   int o = 0;
-  s.x = take_floats(o, span_max + 64);  // + zeroed slack past the last staged sample
+  // every frame reads N samples from its start (the window is zero past L): N floats of slack
+  s.x = take_floats(o, span_max + N);
   s.w = take_floats(o, N);
   s.scr = take_floats(o, 2 * (kThreads / G) * G * (R1 + 1));
   s.P = take_floats(o, (K + 7) * kTileStride);  // + zero rows read by the 4-tap band padding
   s.e = take_floats(o, kTileFrames);
+  s.out = take_floats(o, kTileFrames * C);
+  s.bar = take_floats(o, 4);
   s.lo = take_floats(o, F);
   s.n4 = take_floats(o, F);
   s.off = take_floats(o, F);
@@ -176,7 +219,17 @@ __host__ __device__ inline SmemLayout fused_layout(int N, int G, int R1, int spa
 // ------------------------------------------------------------------------------------------
 // the fused kernel
 // ------------------------------------------------------------------------------------------
-template <int N, bool POWER, typename T>
+// How the stage-1 loads are specialised at compile time (no per-row branches in the hot loop):
+//   kRows13  : ceil(L / 2G) == 13 R1/16 rows carry data (25 ms frames in a 32 ms DFT and the
+//              like); the remaining rows are exact zeros and are never loaded
+//   kRows16  : ceil(L / 2G) == R1 (L close or equal to N)
+//   kRowsAny : any L <= N: all rows are loaded (the zero-padded window annihilates the tail) and
+//              the energy is masked element by element
+// In the first two modes only the LAST row can be partially filled; two per-thread predicates
+// computed once per kernel mask its samples out of the energy.
+enum RowMode { kRows13 = 0, kRows16 = 1, kRowsAny = 2 };
+
+template <int N, bool POWER, typename T, int MODE>
 __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
     stft_fused_kernel(const __grid_constant__ StftParams p) {
   using Geo = FftGeom<N>;
@@ -185,19 +238,22 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
   constexpr int FPR = kThreads / G;  // frames per round
   constexpr bool REGTW = (R1 <= 16);
   constexpr int TS = kTileStride;
+  constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
 
   extern __shared__ __align__(16) float smem[];
-  const SmemLayout lay = fused_layout(N, G, R1, p.span_max, p.F, p.weights_in_smem ? p.weights_total : 0);
+  const SmemLayout lay =
+      fused_layout(N, G, R1, p.span_max, p.F, p.C, p.weights_in_smem ? p.weights_total : 0);
   float* s_x = smem + lay.x;
   float* s_w = smem + lay.w;
   float2* s_scr = reinterpret_cast<float2*>(smem + lay.scr);
   float* s_P = smem + lay.P;
   float* s_e = smem + lay.e;
+  float* s_out = smem + lay.out;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + lay.bar);
   int* s_lo = reinterpret_cast<int*>(smem + lay.lo);
   int* s_n4 = reinterpret_cast<int*>(smem + lay.n4);
   int* s_off = reinterpret_cast<int*>(smem + lay.off);
   float* s_wt = smem + lay.wt;
-  float* s_out = s_x;  // the staged samples are dead once the fft phase is over
 
   const int tid = threadIdx.x;
   const int sub = tid / G, l = tid % G;
@@ -212,7 +268,11 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
   if (p.weights_in_smem)
     for (int i = tid; i < p.weights_total; i += kThreads) s_wt[i] = p.weights[i];
   for (int i = tid; i < 7 * TS; i += kThreads) s_P[K * TS + i] = 0.f;  // padding rows
-  for (int i = tid; i < 64; i += kThreads) s_x[p.span_max + i] = 0.f;
+  for (int i = tid; i < p.span_max + N; i += kThreads) s_x[i] = 0.f;   // slack must stay finite
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   const float* bank_weights = p.weights_in_smem ? s_wt : p.weights;
 
   float2 tw_stage[REGTW ? R1 : 1], tw_split[REGTW ? R1 / 2 : 1];
@@ -222,17 +282,41 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
 #pragma unroll
     for (int m = 0; m < R1 / 2; ++m) tw_split[m] = p.tw_split[l * (R1 / 2) + m];
   }
+  // validity of this lane's two samples in the last loaded row (modes kRows13 / kRows16)
+  const bool last_ok0 = 2 * (G * (ROWS - 1) + l) < p.L;
+  const bool last_ok1 = 2 * (G * (ROWS - 1) + l) + 1 < p.L;
   const int partner = (G - l) % G;
   float2* scr = s_scr + sub * Geo::SCR_FLOAT2;
+  const bool want_energy = p.include_energy != 0;
   __syncthreads();
 
-  for (long long tile_idx = blockIdx.x; tile_idx < p.n_tiles; tile_idx += gridDim.x) {
-    const pds_tile tile = p.tiles[tile_idx];
-    const int nframes = tile.nframes;
-    const int span = (nframes - 1) * p.S + p.L;
+  // ---- stage the first tile --------------------------------------------------------------
+  uint32_t bar_parity = 0;
+  bool pending_bulk = false;  // uniform: the current tile's samples arrive through the mbarrier
+  long long tile_idx = blockIdx.x;
+  pds_tile tile;
+  if (tile_idx < p.n_tiles) {
+    tile = p.tiles[tile_idx];
+    const int span = (tile.nframes - 1) * p.S + p.L;
+    pending_bulk = tile_is_bulk<T>(p, tile, span);
+    if (pending_bulk) {
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // zero-fill above -> async proxy
+        mbar_expect_tx(s_bar, span * 4);
+        bulk_copy_g2s(s_x, static_cast<const T*>(p.sig) + tile.sig_off + tile.start, span * 4, s_bar);
+      }
+    } else {
+      stage_samples_slow<T, kThreads>(s_x, p, tile, span);
+      __syncthreads();
+    }
+  }
 
-    stage_samples<T, kThreads>(s_x, p, tile, span);
-    __syncthreads();
+  for (; tile_idx < p.n_tiles; tile_idx += gridDim.x) {
+    const int nframes = tile.nframes;
+    if (pending_bulk) {
+      mbar_wait(s_bar, bar_parity);
+      bar_parity ^= 1;
+    }
 
     // ---- fft phase ---------------------------------------------------------------------
     for (int t0 = 0; t0 < nframes; t0 += FPR) {
@@ -246,24 +330,24 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
       float energy = 0.f;
 #pragma unroll
       for (int r = 0; r < R1; ++r) {
-        if (r < p.rows_full) {
-          const float2 x = xp[G * r], w = wp[G * r];
+        if (r < ROWS) {
+          float2 x = xp[G * r];
+          const float2 w = wp[G * r];
+          z[r] = make_float2(x.x * w.x, x.y * w.y);
+          if (MODE == kRowsAny) {
+            x.x = 2 * (G * r + l) < p.L ? x.x : 0.f;
+            x.y = 2 * (G * r + l) + 1 < p.L ? x.y : 0.f;
+          } else if (r == ROWS - 1) {
+            x.x = last_ok0 ? x.x : 0.f;
+            x.y = last_ok1 ? x.y : 0.f;
+          }
           energy = fmaf(x.x, x.x, energy);
           energy = fmaf(x.y, x.y, energy);
-          z[r] = make_float2(x.x * w.x, x.y * w.y);
-        } else if (r == p.rows_full && p.row_partial) {
-          const int i0 = 2 * (G * r + l);
-          const float x0 = i0 < p.L ? fx[i0] : 0.f;
-          const float x1 = i0 + 1 < p.L ? fx[i0 + 1] : 0.f;
-          const float2 w = wp[G * r];
-          energy = fmaf(x0, x0, energy);
-          energy = fmaf(x1, x1, energy);
-          z[r] = make_float2(x0 * w.x, x1 * w.y);
         } else {
           z[r] = make_float2(0.f, 0.f);
         }
       }
-      if (p.include_energy) {
+      if (want_energy) {
 #pragma unroll
         for (int off = G / 2; off > 0; off >>= 1) energy += __shfl_xor_sync(0xffffffffu, energy, off, G);
         if (l == 0) s_e[t] = energy;
@@ -316,17 +400,38 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
         pcol[(NC / 2) * TS] = pk;
       }
     }
-    __syncthreads();
+    __syncthreads();  // s_x is free again, s_P / s_e are complete
+
+    // ---- prefetch the next tile's samples while this tile goes through bank + store ----
+    const pds_tile cur = tile;
+    const long long next_idx = tile_idx + gridDim.x;
+    bool next_slow = false;
+    int next_span = 0;
+    pending_bulk = false;
+    if (next_idx < p.n_tiles) {
+      tile = p.tiles[next_idx];
+      next_span = (tile.nframes - 1) * p.S + p.L;
+      pending_bulk = tile_is_bulk<T>(p, tile, next_span);
+      next_slow = !pending_bulk;
+      if (pending_bulk && tid == 0) {
+        // order the generic-proxy reads of s_x above before the async-proxy write
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(s_bar, next_span * 4);
+        bulk_copy_g2s(s_x, static_cast<const T*>(p.sig) + tile.sig_off + tile.start, next_span * 4, s_bar);
+      }
+    }
 
     // ---- filter bank + log -------------------------------------------------------------
     bank_phase<kThreads, TS>(s_P, s_e, s_out, bank_weights, s_lo, s_n4, s_off, p, POWER);
+    if (next_slow) stage_samples_slow<T, kThreads>(s_x, p, tile, next_span);
     __syncthreads();
 
     // ---- coalesced store ---------------------------------------------------------------
-    float* __restrict__ dst = p.out + tile.out_row * p.C;
+    float* __restrict__ dst = p.out + cur.out_row * p.C;
     const int total = nframes * p.C;
     for (int i = tid; i < total; i += kThreads) dst[i] = s_out[i];
-    __syncthreads();
+    // no barrier here: the next fft phase only touches s_x / s_P / s_e, and s_out is not written
+    // again before the barrier that follows that phase
   }
 }
 
@@ -413,6 +518,7 @@ struct pds_stft_plan {
   int L = 0, S = 0, N = 0, K = 0, F = 0, C = 0, pad_left = 0;
   bool fast = false;
   bool power = false;
+  int row_mode = 2;
   int tile_frames = 0;
   int G = 0, R1 = 0;
   size_t smem_bytes = 0;
@@ -432,37 +538,33 @@ namespace {
 
 using KernelFn = void (*)(const StftParams);
 
+template <int N, int MODE>
+KernelFn pick_fused_mode(bool power, int dtype) {
+  if (power) return dtype == PDS_I16 ? stft_fused_kernel<N, true, short, MODE> : stft_fused_kernel<N, true, float, MODE>;
+  return dtype == PDS_I16 ? stft_fused_kernel<N, false, short, MODE> : stft_fused_kernel<N, false, float, MODE>;
+}
+
 template <int N>
-KernelFn pick_fused(bool power, int dtype) {
-  if (power) {
-    if (dtype == PDS_F32) return stft_fused_kernel<N, true, float>;
-    if (dtype == PDS_I16) return stft_fused_kernel<N, true, short>;
-    return stft_fused_kernel<N, true, double>;
+KernelFn pick_fused(bool power, int dtype, int mode) {
+  switch (mode) {
+    case kRows13: return pick_fused_mode<N, kRows13>(power, dtype);
+    case kRows16: return pick_fused_mode<N, kRows16>(power, dtype);
+    default: return pick_fused_mode<N, kRowsAny>(power, dtype);
   }
-  if (dtype == PDS_F32) return stft_fused_kernel<N, false, float>;
-  if (dtype == PDS_I16) return stft_fused_kernel<N, false, short>;
-  return stft_fused_kernel<N, false, double>;
 }
 
 KernelFn pick_kernel(const pds_stft_plan* plan, int dtype) {
   if (plan->fast) {
     switch (plan->N) {
-      case 128: return pick_fused<128>(plan->power, dtype);
-      case 256: return pick_fused<256>(plan->power, dtype);
-      case 512: return pick_fused<512>(plan->power, dtype);
-      case 1024: return pick_fused<1024>(plan->power, dtype);
-      case 2048: return pick_fused<2048>(plan->power, dtype);
+      case 256: return pick_fused<256>(plan->power, dtype, plan->row_mode);
+      case 512: return pick_fused<512>(plan->power, dtype, plan->row_mode);
+      case 1024: return pick_fused<1024>(plan->power, dtype, plan->row_mode);
+      case 2048: return pick_fused<2048>(plan->power, dtype, plan->row_mode);
       default: return nullptr;
     }
   }
-  if (plan->power) {
-    if (dtype == PDS_F32) return stft_direct_kernel<true, float>;
-    if (dtype == PDS_I16) return stft_direct_kernel<true, short>;
-    return stft_direct_kernel<true, double>;
-  }
-  if (dtype == PDS_F32) return stft_direct_kernel<false, float>;
-  if (dtype == PDS_I16) return stft_direct_kernel<false, short>;
-  return stft_direct_kernel<false, double>;
+  if (plan->power) return dtype == PDS_I16 ? stft_direct_kernel<true, short> : stft_direct_kernel<true, float>;
+  return dtype == PDS_I16 ? stft_direct_kernel<false, short> : stft_direct_kernel<false, float>;
 }
 
 void geometry_for(int N, int* G, int* R1) {
@@ -471,7 +573,7 @@ void geometry_for(int N, int* G, int* R1) {
   *R1 = NC / *G;
 }
 
-size_t dtype_size(int dtype) { return dtype == PDS_I16 ? 2 : (dtype == PDS_F64 ? 8 : 4); }
+size_t dtype_size(int dtype) { return dtype == PDS_I16 ? 2 : 4; }
 
 }  // namespace
 
@@ -527,16 +629,18 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   // ---- pick the kernel: shared-memory FFT when the geometry allows, else direct DFT ------
   StftParams& p = plan->params;
   const bool pow2 = (N & (N - 1)) == 0;
-  plan->fast = pow2 && N >= 128 && N <= 2048 && (S % 2 == 0);
+  plan->fast = pow2 && N >= 256 && N <= 2048 && (S % 2 == 0);
   if (plan->fast) {
     geometry_for(N, &plan->G, &plan->R1);
     const int G = plan->G, R1 = plan->R1;
+    const int rows = (L + 2 * G - 1) / (2 * G);  // stage-1 rows that carry samples
+    plan->row_mode = rows == R1 ? kRows16 : (rows == (R1 * 13) / 16 ? kRows13 : kRowsAny);
     p.rows_full = L / (2 * G);
     p.row_partial = (L % (2 * G)) != 0;
-    p.span_max = std::max((kTileFrames - 1) * S + L, kTileFrames * plan->C);  // s_out aliases s_x
+    p.span_max = (kTileFrames - 1) * S + L;
     // keep the weights in shared memory while that still leaves room for two CTAs per SM
-    const SmemLayout with = fused_layout(N, G, R1, p.span_max, F, wtotal);
-    const SmemLayout without = fused_layout(N, G, R1, p.span_max, F, 0);
+    const SmemLayout with = fused_layout(N, G, R1, p.span_max, F, plan->C, wtotal);
+    const SmemLayout without = fused_layout(N, G, R1, p.span_max, F, plan->C, 0);
     p.weights_in_smem = (size_t)with.total <= std::min<size_t>(smem_cap, 110 * 1024) ? 1 : 0;
     plan->smem_bytes = p.weights_in_smem ? with.total : without.total;
     if (plan->smem_bytes > smem_cap) plan->fast = false;  // huge frame shift: use the direct kernel
@@ -627,7 +731,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   p.dither_first = d->dither_first ? 1 : 0;
 
   // opt in to the dynamic shared memory for every instantiation this plan may launch
-  for (int dt = 0; dt < 3; ++dt) {
+  for (int dt = 0; dt < 2; ++dt) {
     KernelFn fn = pick_kernel(plan, dt);
     err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn),
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
@@ -728,8 +832,8 @@ extern "C" int pds_stft_run(pds_stft_plan* plan, const void* d_signal, int sig_d
                             const pds_tile* d_tiles, int64_t n_tiles, float* d_out, uint64_t seed,
                             void* stream) {
   PDS_REQUIRE(plan, "null plan");
-  PDS_REQUIRE(sig_dtype == PDS_F32 || sig_dtype == PDS_I16 || sig_dtype == PDS_F64,
-              "unknown sample dtype %d", sig_dtype);
+  PDS_REQUIRE(sig_dtype == PDS_F32 || sig_dtype == PDS_I16,
+              "sample dtype %d is not float32 / int16 (convert float64 on the host side)", sig_dtype);
   if (n_tiles == 0) return PDS_OK;
   PDS_REQUIRE(d_signal && d_tiles && d_out && n_tiles > 0, "null buffer");
   StftParams p = plan->params;
@@ -763,8 +867,8 @@ extern "C" int pds_stft_compute_host(pds_stft_plan* plan, const void* h_signal, 
                                      const int64_t* sig_len, float* h_out, int64_t out_capacity_rows,
                                      int64_t* frame_off, uint64_t seed) {
   PDS_REQUIRE(plan && sig_off && sig_len && frame_off && n_utts >= 0 && total_samples >= 0, "bad argument");
-  PDS_REQUIRE(sig_dtype == PDS_F32 || sig_dtype == PDS_I16 || sig_dtype == PDS_F64,
-              "unknown sample dtype %d", sig_dtype);
+  PDS_REQUIRE(sig_dtype == PDS_F32 || sig_dtype == PDS_I16,
+              "sample dtype %d is not float32 / int16 (convert float64 on the host side)", sig_dtype);
   for (int64_t u = 0; u < n_utts; ++u)
     PDS_REQUIRE(sig_off[u] >= 0 && sig_off[u] + sig_len[u] <= total_samples,
                 "utterance %lld lies outside the packed buffer", (long long)u);

@@ -87,7 +87,8 @@ def test_cmvn_errors_and_io(speech, tmp_path):
     with pytest.raises(ValueError, match="global statistics"):
         std.apply(np.ones(4))
     rng = np.random.default_rng(2)
-    std.accumulate(rng.standard_normal((100, 4)), axis=1)
+    # (the reference's raw-binary sanity check rejects negative sums, post.py:130-131)
+    std.accumulate(rng.standard_normal((100, 4)) + 5.0, axis=1)
     with pytest.raises(ValueError, match="Expected feature vector of length 4; got 5"):
         std.accumulate(np.ones((3, 5)))
     for name in ("stats.npy", "stats.npz", "stats.bin"):
