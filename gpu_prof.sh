@@ -1,14 +1,7 @@
 #!/bin/bash
-# ncu session: launch list of the bench command + one full capture of the fused kernel
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
-CMD="python bench.py --steps 3 --warmup 3 --utts 2000 --no-e2e --no-cpu"
-$CMD > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
-echo "launch list rc=$?"
 CMD2="python tools/probe_stft.py 600"
 $CMD2 > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:stft_fused -s 3 -c 2 -o gpurun_out/prof_stft -f $CMD2 > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:stft_fused -s 3 -c 1 -o gpurun_out/prof_stft -f $CMD2 > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"; tail -3 gpurun_out/ncu_full.log
-ls -la gpurun_out
