@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -x -q -m gpu --durations=8 > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -22 gpurun_out/pytest_gpu.log
-timeout 300 python tools/probe_stft.py 2000 > gpurun_out/probe.log 2>&1; tail -4 gpurun_out/probe.log
+timeout 200 python -m pytest tests/test_gpu_stft.py -x -q -m gpu > gpurun_out/pytest_ws.log 2>&1
+echo "stft pytest rc=$?"; tail -3 gpurun_out/pytest_ws.log
+PDS_STFT_KERNEL=phased timeout 60 python tools/probe_stft.py 2000 > gpurun_out/probe_phased.log 2>&1; echo "probe rc=$?"; tail -3 gpurun_out/probe_phased.log
+PDS_STFT_KERNEL=ws timeout 60 python tools/probe_stft.py 2000 > gpurun_out/probe.log 2>&1; echo "probe rc=$?"; tail -3 gpurun_out/probe.log

@@ -21,6 +21,7 @@
 // stft_direct_kernel, a plain O(L*K) DFT per frame with the same staging and bank code.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -48,10 +49,15 @@ struct StftParams {
   const int* band_lo;       // [F]
   const int* band_n4;       // [F] taps / 4 after zero padding to a multiple of 8
   const int* band_off;      // [F] offset (floats, multiple of 4) into weights
-  const int4* band_desc;    // [F] {lo * kTileStride, taps / 8, weight offset, output column}
-  const float* weights;     // padded taps
-  int weights_total;        // floats in `weights`
+  const float* weights;     // padded taps, one filter after the other (direct kernel)
+  // fused kernels: filters are processed two at a time (ILP); both members of a pair are padded
+  // to the same number of 8-tap groups and their weights interleaved group by group
+  const int4* pair_desc;    // [npairs] {lo_a * kTileStride, lo_b * kTileStride, groups, weight offset}
+  const float* pair_weights;
+  int npairs;
+  int weights_total;        // floats in `pair_weights`
   int weights_in_smem;
+  int p_rows;               // rows of the power-spectrum tile: K bins + zero rows read by the padding
   int L, S, N, K, F, C;
   int rows_full, row_partial;  // L / (2G) full rows of the stage-1 load, and whether one more is partial
   int span_max;                // floats reserved for the staged samples
@@ -89,18 +95,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
   asm volatile(
       "{\n"
-      ".reg .pred done;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n"
-      "@done bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return done != 0;
+}
+// Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1u << 22)) __trap();
 }
 __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -152,45 +163,162 @@ __device__ __forceinline__ float fast_log(float x) {
 // ------------------------------------------------------------------------------------------
 // filter-bank phase: lane = frame, each warp takes every (blockDim/32)-th filter
 // ------------------------------------------------------------------------------------------
-template <int THREADS, int STRIDE>
-__device__ __forceinline__ void bank_phase(const float* __restrict__ s_P,
-                                           const float* __restrict__ s_e,
-                                           float* __restrict__ s_out,
+// `group_warp` of `NWARPS` cooperating warps; lane = frame.  Two filters (2 pi, 2 pi + 1) per trip.
+template <int NWARPS, int STRIDE>
+__device__ __forceinline__ void bank_pairs(int group_warp, int lane, const float* __restrict__ s_P,
+                                           const float* __restrict__ s_e, float* __restrict__ s_out,
                                            const float* __restrict__ weights,
                                            const int4* __restrict__ s_desc, const StftParams& p,
                                            bool power) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool use_log = p.use_log != 0;
   const float log_floor = p.log_floor;
-  float* __restrict__ out_row = s_out + lane * p.C;
-  for (int f = warp; f < p.F; f += THREADS / 32) {
-    const int4 d = s_desc[f];  // one broadcast load per filter
-    const float4* __restrict__ wt = reinterpret_cast<const float4*>(weights + d.z);
-    const float* __restrict__ pp = s_P + d.x + lane;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-    for (int j = 0; j < d.y; ++j) {  // eight taps per trip, loads first: four independent chains
-      const float4 wa = wt[2 * j], wb = wt[2 * j + 1];
-      const float p0 = pp[0], p1 = pp[STRIDE], p2 = pp[2 * STRIDE], p3 = pp[3 * STRIDE];
-      const float p4 = pp[4 * STRIDE], p5 = pp[5 * STRIDE], p6 = pp[6 * STRIDE], p7 = pp[7 * STRIDE];
-      acc0 = fmaf(p0, wa.x, acc0);
-      acc1 = fmaf(p1, wa.y, acc1);
-      acc2 = fmaf(p2, wa.z, acc2);
-      acc3 = fmaf(p3, wa.w, acc3);
-      acc0 = fmaf(p4, wb.x, acc0);
-      acc1 = fmaf(p5, wb.y, acc1);
-      acc2 = fmaf(p6, wb.z, acc2);
-      acc3 = fmaf(p7, wb.w, acc3);
-      pp += 8 * STRIDE;
+  float* __restrict__ out_row = s_out + lane * p.C + p.include_energy;
+  for (int pi = group_warp; pi < p.npairs; pi += NWARPS) {
+    const int4 d = s_desc[pi];  // one broadcast load per pair
+    const float4* __restrict__ wt = reinterpret_cast<const float4*>(weights + d.w);
+    const float* __restrict__ pa = s_P + d.x + lane;
+    const float* __restrict__ pb = s_P + d.y + lane;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+    for (int j = 0; j < d.z; ++j) {  // 16 taps per trip, all 20 loads issued before the FMAs
+      const float4 wa0 = wt[0], wa1 = wt[1], wb0 = wt[2], wb1 = wt[3];
+      const float x0 = pa[0], x1 = pa[STRIDE], x2 = pa[2 * STRIDE], x3 = pa[3 * STRIDE];
+      const float x4 = pa[4 * STRIDE], x5 = pa[5 * STRIDE], x6 = pa[6 * STRIDE], x7 = pa[7 * STRIDE];
+      const float y0 = pb[0], y1 = pb[STRIDE], y2 = pb[2 * STRIDE], y3 = pb[3 * STRIDE];
+      const float y4 = pb[4 * STRIDE], y5 = pb[5 * STRIDE], y6 = pb[6 * STRIDE], y7 = pb[7 * STRIDE];
+      a0 = fmaf(x0, wa0.x, a0);
+      a1 = fmaf(x1, wa0.y, a1);
+      a2 = fmaf(x2, wa0.z, a2);
+      a3 = fmaf(x3, wa0.w, a3);
+      b0 = fmaf(y0, wb0.x, b0);
+      b1 = fmaf(y1, wb0.y, b1);
+      b2 = fmaf(y2, wb0.z, b2);
+      b3 = fmaf(y3, wb0.w, b3);
+      a0 = fmaf(x4, wa1.x, a0);
+      a1 = fmaf(x5, wa1.y, a1);
+      a2 = fmaf(x6, wa1.z, a2);
+      a3 = fmaf(x7, wa1.w, a3);
+      b0 = fmaf(y4, wb1.x, b0);
+      b1 = fmaf(y5, wb1.y, b1);
+      b2 = fmaf(y6, wb1.z, b2);
+      b3 = fmaf(y7, wb1.w, b3);
+      wt += 4;
+      pa += 8 * STRIDE;
+      pb += 8 * STRIDE;
     }
-    float v = (acc0 + acc1) + (acc2 + acc3);
-    if (use_log) v = fast_log(fmaxf(v, log_floor));
-    out_row[d.w] = v;
+    float va = (a0 + a1) + (a2 + a3), vb = (b0 + b1) + (b2 + b3);
+    if (use_log) {
+      va = fast_log(fmaxf(va, log_floor));
+      vb = fast_log(fmaxf(vb, log_floor));
+    }
+    out_row[2 * pi] = va;
+    if (2 * pi + 1 < p.F) out_row[2 * pi + 1] = vb;
   }
-  if (p.include_energy && warp == 0) {
+  if (p.include_energy && group_warp == 0) {
     float v = s_e[lane] * p.inv_L;
     if (!power) v = sqrtf(v);
     if (use_log) v = fast_log(fmaxf(v, log_floor));
-    out_row[0] = v;
+    s_out[lane * p.C] = v;
+  }
+}
+
+// How the stage-1 loads are specialised at compile time (no per-row branches in the hot loop):
+//   kRows13  : ceil(L / 2G) == 13 R1/16 rows carry data (25 ms frames in a 32 ms DFT and the
+//              like); the remaining rows are exact zeros and are never loaded
+//   kRows16  : ceil(L / 2G) == R1 (L close or equal to N)
+//   kRowsAny : any L <= N: all rows are loaded (the zero-padded window annihilates the tail) and
+//              the energy is masked element by element
+// In the first two modes only the LAST row can be partially filled; two per-thread predicates
+// computed once per kernel mask its samples out of the energy.
+enum RowMode { kRows13 = 0, kRows16 = 1, kRowsAny = 2 };
+
+// ------------------------------------------------------------------------------------------
+// one frame on one sub-group of G lanes: window, energy, two-stage FFT, split, |X|^p -> pcol
+// ------------------------------------------------------------------------------------------
+template <int N, bool POWER, int MODE, int NTW, int NTS>
+__device__ __forceinline__ void fft_frame(const float* __restrict__ fx, const float* __restrict__ s_w,
+                                          float2* __restrict__ scr, float* __restrict__ pcol,
+                                          float* __restrict__ e_slot, const float2 (&tw_stage)[NTW],
+                                          const float2 (&tw_split)[NTS], int l, bool last_ok0,
+                                          bool last_ok1, bool want_energy, const StftParams& p) {
+  using Geo = FftGeom<N>;
+  constexpr int NC = Geo::NC, G = Geo::G, R1 = Geo::R1, NSUB = Geo::NSUB;
+  constexpr bool REGTW = (R1 <= 16);
+  constexpr int TS = kTileStride;
+  constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
+  const int partner = (G - l) % G;
+  const float2* xp = reinterpret_cast<const float2*>(fx) + l;
+  const float2* wp = reinterpret_cast<const float2*>(s_w) + l;
+  float2 z[R1];
+  float energy = 0.f;
+#pragma unroll
+  for (int r = 0; r < R1; ++r) {
+    if (r < ROWS) {
+      float2 x = xp[G * r];
+      const float2 w = wp[G * r];
+      z[r] = make_float2(x.x * w.x, x.y * w.y);
+      if (MODE == kRowsAny) {
+        x.x = 2 * (G * r + l) < p.L ? x.x : 0.f;
+        x.y = 2 * (G * r + l) + 1 < p.L ? x.y : 0.f;
+      } else if (r == ROWS - 1) {
+        x.x = last_ok0 ? x.x : 0.f;
+        x.y = last_ok1 ? x.y : 0.f;
+      }
+      energy = fmaf(x.x, x.x, energy);
+      energy = fmaf(x.y, x.y, energy);
+    } else {
+      z[r] = make_float2(0.f, 0.f);
+    }
+  }
+  if (want_energy) {
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) energy += __shfl_xor_sync(0xffffffffu, energy, off, G);
+    if (l == 0) *e_slot = energy;
+  }
+
+  Dft<R1>::run(z);
+#pragma unroll
+  for (int k1 = 1; k1 < R1; ++k1)
+    z[k1] = cmul(z[k1], REGTW ? tw_stage[k1] : __ldg(&p.tw_stage[l * R1 + k1]));
+#pragma unroll
+  for (int k1 = 0; k1 < R1; ++k1) scr[l * Geo::SCR_STRIDE + k1] = z[k1];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < NSUB; ++j) {
+    float2 v[G];
+#pragma unroll
+    for (int n2 = 0; n2 < G; ++n2) v[n2] = scr[n2 * Geo::SCR_STRIDE + l + G * j];
+    Dft<G>::run(v);
+#pragma unroll
+    for (int k2 = 0; k2 < G; ++k2) z[j + NSUB * k2] = v[k2];
+  }
+  __syncwarp();
+
+  // real-FFT split: lane l pairs its lower-half registers with the partner's upper half
+#pragma unroll
+  for (int m = 0; m < R1 / 2; ++m) {
+    float2 b;
+    b.x = __shfl_sync(0xffffffffu, z[R1 - 1 - m].x, partner, G);
+    b.y = __shfl_sync(0xffffffffu, z[R1 - 1 - m].y, partner, G);
+    if (l == 0) b = z[(R1 - m) % R1];
+    const float2 w = REGTW ? tw_split[m] : __ldg(&p.tw_split[l * (R1 / 2) + m]);
+    float2 xk, xq;
+    split_pair(z[m], b, w, xk, xq);
+    float pk = xk.x * xk.x + xk.y * xk.y, pq = xq.x * xq.x + xq.y * xq.y;
+    if (!POWER) {
+      pk = sqrtf(pk);
+      pq = sqrtf(pq);
+    }
+    const int k = l + G * m;
+    pcol[k * TS] = pk;
+    pcol[(NC - k) * TS] = pq;
+  }
+  if (l == 0) {  // bin NC/2 pairs with itself; its twiddle is -i
+    const float2 a = z[R1 / 2];
+    float2 xk, xq;
+    split_pair(a, a, make_float2(0.f, -1.f), xk, xq);
+    float pk = xk.x * xk.x + xk.y * xk.y;
+    if (!POWER) pk = sqrtf(pk);
+    pcol[(NC / 2) * TS] = pk;
   }
 }
 
@@ -205,20 +333,19 @@ __host__ __device__ inline int take_floats(int& cursor, int n) {
   return at;
 }
 
-__host__ __device__ inline SmemLayout fused_layout(int N, int G, int R1, int span_max, int F, int C,
-                                                   int weights_floats) {
+__host__ __device__ inline SmemLayout fused_layout(int N, int G, int R1, int span_max, int p_rows,
+                                                   int npairs, int C, int weights_floats) {
   SmemLayout s;
-  const int K = N / 2 + 1;
   int o = 0;
   // every frame reads N samples from its start (the window is zero past L): N floats of slack
   s.x = take_floats(o, span_max + N);
   s.w = take_floats(o, N);
   s.scr = take_floats(o, 2 * (kThreads / G) * G * (R1 + 1));
-  s.P = take_floats(o, (K + 7) * kTileStride);  // + zero rows read by the 8-tap band padding
+  s.P = take_floats(o, p_rows * kTileStride);
   s.e = take_floats(o, kTileFrames);
   s.out = take_floats(o, kTileFrames * C);
   s.bar = take_floats(o, 4);
-  s.desc = take_floats(o, 4 * F);
+  s.desc = take_floats(o, 4 * npairs);
   s.wt = take_floats(o, weights_floats);
   s.total = o * 4;
   return s;
@@ -227,16 +354,6 @@ __host__ __device__ inline SmemLayout fused_layout(int N, int G, int R1, int spa
 // ------------------------------------------------------------------------------------------
 // the fused kernel
 // ------------------------------------------------------------------------------------------
-// How the stage-1 loads are specialised at compile time (no per-row branches in the hot loop):
-//   kRows13  : ceil(L / 2G) == 13 R1/16 rows carry data (25 ms frames in a 32 ms DFT and the
-//              like); the remaining rows are exact zeros and are never loaded
-//   kRows16  : ceil(L / 2G) == R1 (L close or equal to N)
-//   kRowsAny : any L <= N: all rows are loaded (the zero-padded window annihilates the tail) and
-//              the energy is masked element by element
-// In the first two modes only the LAST row can be partially filled; two per-thread predicates
-// computed once per kernel mask its samples out of the energy.
-enum RowMode { kRows13 = 0, kRows16 = 1, kRowsAny = 2 };
-
 template <int N, bool POWER, typename T, int MODE>
 __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
     stft_fused_kernel(const __grid_constant__ StftParams p) {
@@ -250,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
 
   extern __shared__ __align__(16) float smem[];
   const SmemLayout lay =
-      fused_layout(N, G, R1, p.span_max, p.F, p.C, p.weights_in_smem ? p.weights_total : 0);
+      fused_layout(N, G, R1, p.span_max, p.p_rows, p.npairs, p.C, p.weights_in_smem ? p.weights_total : 0);
   float* s_x = smem + lay.x;
   float* s_w = smem + lay.w;
   float2* s_scr = reinterpret_cast<float2*>(smem + lay.scr);
@@ -266,16 +383,16 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
 
   // ---- one-time CTA set-up -------------------------------------------------------------
   for (int i = tid; i < N; i += kThreads) s_w[i] = p.window[i];
-  for (int i = tid; i < p.F; i += kThreads) s_desc[i] = p.band_desc[i];
+  for (int i = tid; i < p.npairs; i += kThreads) s_desc[i] = p.pair_desc[i];
   if (p.weights_in_smem)
-    for (int i = tid; i < p.weights_total; i += kThreads) s_wt[i] = p.weights[i];
-  for (int i = tid; i < 7 * TS; i += kThreads) s_P[K * TS + i] = 0.f;  // padding rows
+    for (int i = tid; i < p.weights_total; i += kThreads) s_wt[i] = p.pair_weights[i];
+  for (int i = tid; i < (p.p_rows - K) * TS; i += kThreads) s_P[K * TS + i] = 0.f;  // padding rows
   for (int i = tid; i < p.span_max + N; i += kThreads) s_x[i] = 0.f;   // slack must stay finite
   if (tid == 0) {
     mbar_init(s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const float* bank_weights = p.weights_in_smem ? s_wt : p.weights;
+  const float* bank_weights = p.weights_in_smem ? s_wt : p.pair_weights;
 
   float2 tw_stage[REGTW ? R1 : 1], tw_split[REGTW ? R1 / 2 : 1];
   if (REGTW) {
@@ -287,7 +404,6 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
   // validity of this lane's two samples in the last loaded row (modes kRows13 / kRows16)
   const bool last_ok0 = 2 * (G * (ROWS - 1) + l) < p.L;
   const bool last_ok1 = 2 * (G * (ROWS - 1) + l) + 1 < p.L;
-  const int partner = (G - l) % G;
   float2* scr = s_scr + sub * Geo::SCR_FLOAT2;
   const bool want_energy = p.include_energy != 0;
   __syncthreads();
@@ -329,82 +445,8 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
       // sub-groups past the end recompute the last frame (identical writes) so that the
       // shuffles below always run with full warps
       const int t = min(t0 + sub, nframes - 1);
-      const float* fx = s_x + t * p.S;
-      const float2* xp = reinterpret_cast<const float2*>(fx) + l;
-      const float2* wp = reinterpret_cast<const float2*>(s_w) + l;
-      float2 z[R1];
-      float energy = 0.f;
-#pragma unroll
-      for (int r = 0; r < R1; ++r) {
-        if (r < ROWS) {
-          float2 x = xp[G * r];
-          const float2 w = wp[G * r];
-          z[r] = make_float2(x.x * w.x, x.y * w.y);
-          if (MODE == kRowsAny) {
-            x.x = 2 * (G * r + l) < p.L ? x.x : 0.f;
-            x.y = 2 * (G * r + l) + 1 < p.L ? x.y : 0.f;
-          } else if (r == ROWS - 1) {
-            x.x = last_ok0 ? x.x : 0.f;
-            x.y = last_ok1 ? x.y : 0.f;
-          }
-          energy = fmaf(x.x, x.x, energy);
-          energy = fmaf(x.y, x.y, energy);
-        } else {
-          z[r] = make_float2(0.f, 0.f);
-        }
-      }
-      if (want_energy) {
-#pragma unroll
-        for (int off = G / 2; off > 0; off >>= 1) energy += __shfl_xor_sync(0xffffffffu, energy, off, G);
-        if (l == 0) s_e[t] = energy;
-      }
-
-      Dft<R1>::run(z);
-#pragma unroll
-      for (int k1 = 1; k1 < R1; ++k1)
-        z[k1] = cmul(z[k1], REGTW ? tw_stage[k1] : __ldg(&p.tw_stage[l * R1 + k1]));
-#pragma unroll
-      for (int k1 = 0; k1 < R1; ++k1) scr[l * Geo::SCR_STRIDE + k1] = z[k1];
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < NSUB; ++j) {
-        float2 v[G];
-#pragma unroll
-        for (int n2 = 0; n2 < G; ++n2) v[n2] = scr[n2 * Geo::SCR_STRIDE + l + G * j];
-        Dft<G>::run(v);
-#pragma unroll
-        for (int k2 = 0; k2 < G; ++k2) z[j + NSUB * k2] = v[k2];
-      }
-      __syncwarp();
-
-      // real-FFT split: lane l pairs its lower-half registers with the partner's upper half
-      float* pcol = s_P + t;
-#pragma unroll
-      for (int m = 0; m < R1 / 2; ++m) {
-        float2 b;
-        b.x = __shfl_sync(0xffffffffu, z[R1 - 1 - m].x, partner, G);
-        b.y = __shfl_sync(0xffffffffu, z[R1 - 1 - m].y, partner, G);
-        if (l == 0) b = z[(R1 - m) % R1];
-        const float2 w = REGTW ? tw_split[m] : __ldg(&p.tw_split[l * (R1 / 2) + m]);
-        float2 xk, xq;
-        split_pair(z[m], b, w, xk, xq);
-        float pk = xk.x * xk.x + xk.y * xk.y, pq = xq.x * xq.x + xq.y * xq.y;
-        if (!POWER) {
-          pk = sqrtf(pk);
-          pq = sqrtf(pq);
-        }
-        const int k = l + G * m;
-        pcol[k * TS] = pk;
-        pcol[(NC - k) * TS] = pq;
-      }
-      if (l == 0) {  // bin NC/2 pairs with itself; its twiddle is -i
-        const float2 a = z[R1 / 2];
-        float2 xk, xq;
-        split_pair(a, a, make_float2(0.f, -1.f), xk, xq);
-        float pk = xk.x * xk.x + xk.y * xk.y;
-        if (!POWER) pk = sqrtf(pk);
-        pcol[(NC / 2) * TS] = pk;
-      }
+      fft_frame<N, POWER, MODE>(s_x + t * p.S, s_w, scr, s_P + t, s_e + t, tw_stage, tw_split, l, last_ok0,
+                                last_ok1, want_energy, p);
     }
     __syncthreads();  // s_x is free again, s_P / s_e are complete
 
@@ -427,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
     }
 
     // ---- filter bank + log -------------------------------------------------------------
-    bank_phase<kThreads, TS>(s_P, s_e, s_out, bank_weights, s_desc, p, POWER);
+    bank_pairs<kThreads / 32, TS>(tid >> 5, tid & 31, s_P, s_e, s_out, bank_weights, s_desc, p, POWER);
     if (next_slow) stage_samples_slow<T, kThreads>(s_x, p, tile, next_span);
     __syncthreads();
 
@@ -437,6 +479,203 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
     for (int i = tid; i < total; i += kThreads) dst[i] = s_out[i];
     // no barrier here: the next fft phase only touches s_x / s_P / s_e, and s_out is not written
     // again before the barrier that follows that phase
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// warp-specialised variant (one CTA per SM, no CTA-wide barriers in steady state)
+//
+//   warps 0..15  fft     : each half-warp owns one frame of every 32-frame tile
+//   warps 16..18 bank    : filter-bank contraction + log + coalesced store of the finished tile
+//   warp  19     producer: TMA bulk copies of the sample spans (cooperative copy at utterance edges)
+//
+// The three roles are coupled only through mbarriers:
+//   x_full[s] / x_empty[s]  sample ring, 2 stages      producer -> fft -> producer
+//   p_full[s] / p_empty[s]  power-spectrum ring, 2 st. fft -> bank -> fft
+// so samples for tile i+1 stream in and tile i-1 goes through the filter bank while the fft warps
+// work on tile i.  Registers are re-balanced with setmaxnreg: the kernel launches with 96 per thread,
+// the bank/producer warpgroup drops to 64 and the 4096 registers it releases into the CTA pool are
+// exactly what the four fft warpgroups need to grow to 104.
+// Used for float32 input without fused pre-processing and G = R1 = 16 (N = 512).
+// ------------------------------------------------------------------------------------------
+constexpr int kWsFftWarps = 16;
+constexpr int kWsBankWarps = 3;
+constexpr int kWsThreads = 32 * (kWsFftWarps + kWsBankWarps + 1);
+
+struct WsLayout {
+  int x, xstride, w, scr, P, pstride, e, out, bar, desc, wt, total;  // floats; total in bytes
+};
+
+__host__ __device__ inline WsLayout ws_layout(int N, int G, int R1, int span_max, int p_rows,
+                                              int npairs, int C, int weights_floats) {
+  WsLayout s;
+  int o = 0;
+  s.xstride = (span_max + N + 3) & ~3;
+  s.x = take_floats(o, 2 * s.xstride);
+  s.w = take_floats(o, N);
+  s.scr = take_floats(o, 2 * (2 * kWsFftWarps) * G * (R1 + 1));
+  s.pstride = (p_rows * kTileStride + 3) & ~3;
+  s.P = take_floats(o, 2 * s.pstride);
+  s.e = take_floats(o, 2 * kTileFrames);
+  s.out = take_floats(o, 2 * kTileFrames * C);
+  s.bar = take_floats(o, 16);
+  s.desc = take_floats(o, 4 * npairs);
+  s.wt = take_floats(o, weights_floats);
+  s.total = o * 4;
+  return s;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int N, bool POWER, int MODE>
+__global__ void __launch_bounds__(kWsThreads, 1) stft_ws_kernel(const __grid_constant__ StftParams p) {
+  using Geo = FftGeom<N>;
+  constexpr int NC = Geo::NC, G = Geo::G, R1 = Geo::R1;
+  static_assert(G == 16 && R1 == 16, "the warp-specialised kernel maps one frame to each half-warp");
+  constexpr int K = NC + 1;
+  constexpr int TS = kTileStride;
+
+  extern __shared__ __align__(16) float smem[];
+  const WsLayout lay = ws_layout(N, G, R1, p.span_max, p.p_rows, p.npairs, p.C, p.weights_total);
+  float* s_x = smem + lay.x;
+  float* s_w = smem + lay.w;
+  float2* s_scr = reinterpret_cast<float2*>(smem + lay.scr);
+  float* s_P = smem + lay.P;
+  float* s_e = smem + lay.e;
+  float* s_out = smem + lay.out;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar);
+  uint64_t* x_full = bars;       // [2]
+  uint64_t* x_empty = bars + 2;  // [2]
+  uint64_t* p_full = bars + 4;   // [2]
+  uint64_t* p_empty = bars + 6;  // [2]
+  int4* s_desc = reinterpret_cast<int4*>(smem + lay.desc);
+  float* s_wt = smem + lay.wt;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time CTA set-up (all roles) ---------------------------------------------------
+  for (int i = tid; i < N; i += kWsThreads) s_w[i] = p.window[i];
+  for (int i = tid; i < p.npairs; i += kWsThreads) s_desc[i] = p.pair_desc[i];
+  for (int i = tid; i < p.weights_total; i += kWsThreads) s_wt[i] = p.pair_weights[i];  // always resident
+  for (int st = 0; st < 2; ++st)
+    for (int i = tid; i < (p.p_rows - K) * TS; i += kWsThreads) s_P[st * lay.pstride + K * TS + i] = 0.f;
+  for (int i = tid; i < 2 * lay.xstride; i += kWsThreads) s_x[i] = 0.f;  // slack must stay finite
+  if (tid == 0) {
+    for (int st = 0; st < 2; ++st) {
+      mbar_init(&x_full[st], 1);
+      mbar_init(&x_empty[st], kWsFftWarps);
+      mbar_init(&p_full[st], kWsFftWarps);
+      mbar_init(&p_empty[st], kWsBankWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long first_tile = blockIdx.x, step = gridDim.x;
+
+  if (warp < kWsFftWarps) {
+    // =============================== fft warps ==========================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int l = lane & 15;
+    float2 tw_stage[R1], tw_split[R1 / 2];
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) tw_stage[k1] = p.tw_stage[l * R1 + k1];
+#pragma unroll
+    for (int m = 0; m < R1 / 2; ++m) tw_split[m] = p.tw_split[l * (R1 / 2) + m];
+    constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
+    const bool last_ok0 = 2 * (G * (ROWS - 1) + l) < p.L;
+    const bool last_ok1 = 2 * (G * (ROWS - 1) + l) + 1 < p.L;
+    const bool want_energy = p.include_energy != 0;
+    float2* scr = s_scr + (2 * warp + (lane >> 4)) * Geo::SCR_FLOAT2;
+    int nframes = first_tile < p.n_tiles ? p.tiles[first_tile].nframes : 0;
+    int it = 0;
+    for (long long tile_idx = first_tile; tile_idx < p.n_tiles; tile_idx += step, ++it) {
+      const int stage = it & 1;
+      const uint32_t phase = (it >> 1) & 1;
+      const int next_nframes = tile_idx + step < p.n_tiles ? p.tiles[tile_idx + step].nframes : 0;
+      mbar_wait(&x_full[stage], phase);
+      if (2 * warp < nframes) {
+        mbar_wait(&p_empty[stage], phase ^ 1);  // the bank warps are done with tile it-2
+        const int t = min(2 * warp + (lane >> 4), nframes - 1);
+        fft_frame<N, POWER, MODE>(s_x + stage * lay.xstride + t * p.S, s_w, scr,
+                                  s_P + stage * lay.pstride + t, s_e + stage * kTileFrames + t, tw_stage,
+                                  tw_split, l, last_ok0, last_ok1, want_energy, p);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&p_full[stage]);
+        mbar_arrive(&x_empty[stage]);
+      }
+      nframes = next_nframes;
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp < kWsFftWarps + kWsBankWarps) {
+      // ============================= bank warps =========================================
+      const int bw = warp - kWsFftWarps;
+      const int bt = tid - 32 * kWsFftWarps;  // 0..95
+      int it = 0;
+      for (long long tile_idx = first_tile; tile_idx < p.n_tiles; tile_idx += step, ++it) {
+        const int stage = it & 1;
+        const uint32_t phase = (it >> 1) & 1;
+        const pds_tile tile = p.tiles[tile_idx];
+        float* out = s_out + stage * kTileFrames * p.C;
+        mbar_wait(&p_full[stage], phase);
+        bank_pairs<kWsBankWarps, TS>(bw, lane, s_P + stage * lay.pstride, s_e + stage * kTileFrames, out,
+                                     s_wt, s_desc, p, POWER);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_empty[stage]);  // this warp no longer reads the P stage
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kWsBankWarps) : "memory");
+        float* __restrict__ dst = p.out + tile.out_row * p.C;
+        const int total = tile.nframes * p.C;
+        for (int i = bt; i < total; i += 32 * kWsBankWarps) dst[i] = out[i];
+        // out[stage] is rewritten two tiles from now, behind the next tile's bar.sync
+      }
+    } else {
+      // ============================= producer warp ======================================
+      const float* __restrict__ sig = static_cast<const float*>(p.sig);
+      int it = 0;
+      for (long long tile_idx = first_tile; tile_idx < p.n_tiles; tile_idx += step, ++it) {
+        const int stage = it & 1;
+        const uint32_t phase = (it >> 1) & 1;
+        const pds_tile tile = p.tiles[tile_idx];
+        const int span = (tile.nframes - 1) * p.S + p.L;
+        float* dst = s_x + stage * lay.xstride;
+        const long long first = tile.start;
+        const float* src = sig + tile.sig_off + first;
+        const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+        const bool bulk = first >= 0 && first + span <= (long long)tile.sig_len && (span & 3) == 0 && aligned;
+        mbar_wait(&x_empty[stage], phase ^ 1);  // the fft warps are done with tile it-2
+        if (bulk) {
+          if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&x_full[stage], span * 4);
+            bulk_copy_g2s(dst, src, span * 4, &x_full[stage]);
+          }
+        } else {
+          // utterance edge: the in-range middle of the span still goes through TMA (when the
+          // packing put it on a 16-byte grid); only the reflected ends are filled by hand
+          const int r0 = (int)max(0LL, -first);
+          const int r1 = (int)min((long long)span, (long long)tile.sig_len - first);
+          int a0 = (r0 + 3) & ~3, a1 = r1 & ~3;
+          if (!aligned || a1 - a0 < 64) a0 = a1 = 0;
+          if (a1 > a0 && lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_copy_g2s(dst + a0, src + a0, (a1 - a0) * 4, &x_full[stage]);
+          }
+          for (int i = lane; i < a0; i += 32) dst[i] = sig[tile.sig_off + reflect_index(first + i, tile.sig_len)];
+          for (int i = a1 + lane; i < span; i += 32)
+            dst[i] = sig[tile.sig_off + reflect_index(first + i, tile.sig_len)];
+          __syncwarp();
+          if (lane == 0) {
+            if (a1 > a0) mbar_expect_tx(&x_full[stage], (a1 - a0) * 4);  // arrival + the bytes in flight
+            else mbar_arrive(&x_full[stage]);
+          }
+        }
+      }
+    }
   }
 }
 
@@ -522,12 +761,15 @@ struct pds_stft_plan {
   int device = 0;
   int L = 0, S = 0, N = 0, K = 0, F = 0, C = 0, pad_left = 0;
   bool fast = false;
+  bool ws = false;  // warp-specialised kernel available (N = 512 geometry, plain float32 input)
+  size_t ws_smem_bytes = 0;
   bool power = false;
   int row_mode = 2;
   int tile_frames = 0;
   int G = 0, R1 = 0;
   size_t smem_bytes = 0;
   int grid_limit = 0;
+  int num_sms = 0;
   StftParams params{};
   void* d_blob = nullptr;  // all constant tables, one allocation
   // scratch for pds_stft_compute_host
@@ -555,6 +797,15 @@ KernelFn pick_fused(bool power, int dtype, int mode) {
     case kRows13: return pick_fused_mode<N, kRows13>(power, dtype);
     case kRows16: return pick_fused_mode<N, kRows16>(power, dtype);
     default: return pick_fused_mode<N, kRowsAny>(power, dtype);
+  }
+}
+
+template <int N>
+KernelFn pick_ws(bool power, int mode) {
+  switch (mode) {
+    case kRows13: return power ? stft_ws_kernel<N, true, kRows13> : stft_ws_kernel<N, false, kRows13>;
+    case kRows16: return power ? stft_ws_kernel<N, true, kRows16> : stft_ws_kernel<N, false, kRows16>;
+    default: return power ? stft_ws_kernel<N, true, kRowsAny> : stft_ws_kernel<N, false, kRowsAny>;
   }
 }
 
@@ -630,13 +881,34 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     off[f] = wtotal;
     wtotal += n4[f] * 4;
   }
-  std::vector<int> desc(4 * (size_t)F);
-  for (int f = 0; f < F; ++f) {
-    desc[4 * f + 0] = lo[f] * kTileStride;
-    desc[4 * f + 1] = n4[f] / 2;
-    desc[4 * f + 2] = off[f];
-    desc[4 * f + 3] = f + (d->include_energy ? 1 : 0);
+  // fused kernels: filter pairs (2i, 2i+1) padded to a common number of 8-tap groups, weights
+  // interleaved per group as [8 taps of a | 8 taps of b]; an odd last filter pairs with zeros
+  const int npairs = (F + 1) / 2;
+  std::vector<int> desc(4 * (size_t)npairs);
+  std::vector<float> pair_wt;
+  int p_rows = K;
+  for (int pi = 0; pi < npairs; ++pi) {
+    const int fa = 2 * pi, fb = std::min(2 * pi + 1, F - 1);
+    const bool has_b = 2 * pi + 1 < F;
+    const int groups = std::max((d->band_len[fa] + 7) / 8, has_b ? (d->band_len[fb] + 7) / 8 : 0);
+    desc[4 * pi + 0] = d->band_lo[fa] * kTileStride;
+    desc[4 * pi + 1] = d->band_lo[fb] * kTileStride;
+    desc[4 * pi + 2] = groups;
+    desc[4 * pi + 3] = (int)pair_wt.size();
+    p_rows = std::max(p_rows, std::max(d->band_lo[fa], d->band_lo[fb]) + 8 * groups);
+    for (int g = 0; g < groups; ++g) {
+      for (int j = 0; j < 8; ++j) {
+        const int t = 8 * g + j;
+        pair_wt.push_back(t < d->band_len[fa] ? d->weights[d->band_off[fa] + t] : 0.f);
+      }
+      for (int j = 0; j < 8; ++j) {
+        const int t = 8 * g + j;
+        pair_wt.push_back(has_b && t < d->band_len[fb] ? d->weights[d->band_off[fb] + t] : 0.f);
+      }
+    }
   }
+  if (pair_wt.empty()) pair_wt.resize(4, 0.f);
+  const int pair_total = (int)pair_wt.size();
 
   // ---- pick the kernel: shared-memory FFT when the geometry allows, else direct DFT ------
   StftParams& p = plan->params;
@@ -651,11 +923,16 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     p.row_partial = (L % (2 * G)) != 0;
     p.span_max = (kTileFrames - 1) * S + L;
     // keep the weights in shared memory while that still leaves room for two CTAs per SM
-    const SmemLayout with = fused_layout(N, G, R1, p.span_max, F, plan->C, wtotal);
-    const SmemLayout without = fused_layout(N, G, R1, p.span_max, F, plan->C, 0);
+    const SmemLayout with = fused_layout(N, G, R1, p.span_max, p_rows, npairs, plan->C, pair_total);
+    const SmemLayout without = fused_layout(N, G, R1, p.span_max, p_rows, npairs, plan->C, 0);
     p.weights_in_smem = (size_t)with.total <= std::min<size_t>(smem_cap, 110 * 1024) ? 1 : 0;
     plan->smem_bytes = p.weights_in_smem ? with.total : without.total;
     if (plan->smem_bytes > smem_cap) plan->fast = false;  // huge frame shift: use the direct kernel
+    if (plan->fast && N == 512 && d->preemph == 0.f && d->dither == 0.f) {
+      const WsLayout ws = ws_layout(N, G, R1, p.span_max, p_rows, npairs, plan->C, pair_total);
+      plan->ws = (size_t)ws.total <= smem_cap;
+      plan->ws_smem_bytes = ws.total;
+    }
   }
   if (!plan->fast) {
     plan->smem_bytes = sizeof(float) * (((L + 3) & ~3) + 2 * (size_t)N + ((K + 7 + 3) & ~3) + 8);
@@ -706,7 +983,8 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   size_t o_n4 = align16(o_lo + sizeof(int) * F);
   size_t o_off = align16(o_n4 + sizeof(int) * F);
   size_t o_desc = align16(o_off + sizeof(int) * F);
-  size_t o_wt = align16(o_desc + sizeof(int) * 4 * F);
+  size_t o_pwt = align16(o_desc + sizeof(int) * 4 * npairs);
+  size_t o_wt = align16(o_pwt + sizeof(float) * pair_wt.size());
   size_t blob_bytes = align16(o_wt + sizeof(float) * wt.size());
   std::vector<unsigned char> blob(blob_bytes, 0);
   std::memcpy(blob.data() + o_win, win.data(), sizeof(float) * N);
@@ -716,7 +994,8 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   std::memcpy(blob.data() + o_lo, lo.data(), sizeof(int) * F);
   std::memcpy(blob.data() + o_n4, n4.data(), sizeof(int) * F);
   std::memcpy(blob.data() + o_off, off.data(), sizeof(int) * F);
-  std::memcpy(blob.data() + o_desc, desc.data(), sizeof(int) * 4 * F);
+  std::memcpy(blob.data() + o_desc, desc.data(), sizeof(int) * 4 * npairs);
+  std::memcpy(blob.data() + o_pwt, pair_wt.data(), sizeof(float) * pair_wt.size());
   std::memcpy(blob.data() + o_wt, wt.data(), sizeof(float) * wt.size());
   err = cudaMalloc(&plan->d_blob, blob_bytes);
   if (err == cudaSuccess) err = cudaMemcpy(plan->d_blob, blob.data(), blob_bytes, cudaMemcpyHostToDevice);
@@ -733,9 +1012,12 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   p.band_lo = reinterpret_cast<const int*>(base + o_lo);
   p.band_n4 = reinterpret_cast<const int*>(base + o_n4);
   p.band_off = reinterpret_cast<const int*>(base + o_off);
-  p.band_desc = reinterpret_cast<const int4*>(base + o_desc);
+  p.pair_desc = reinterpret_cast<const int4*>(base + o_desc);
+  p.pair_weights = reinterpret_cast<const float*>(base + o_pwt);
+  p.npairs = npairs;
+  p.p_rows = p_rows;
   p.weights = reinterpret_cast<const float*>(base + o_wt);
-  p.weights_total = wtotal;
+  p.weights_total = pair_total;
   p.L = L, p.S = S, p.N = N, p.K = K, p.F = F, p.C = plan->C;
   p.include_energy = d->include_energy ? 1 : 0;
   p.use_log = d->use_log ? 1 : 0;
@@ -756,6 +1038,15 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       return PDS_ERR_CUDA;
     }
   }
+  if (plan->ws) {
+    err = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_ws<512>(plan->power, plan->row_mode)),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->ws_smem_bytes);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      plan->ws = false;
+    }
+  }
+  plan->num_sms = prop.multiProcessorCount;
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(pick_kernel(plan, PDS_F32)),
                                                 plan->fast ? kThreads : kDirectThreads, plan->smem_bytes);
@@ -857,6 +1148,17 @@ extern "C" int pds_stft_run(pds_stft_plan* plan, const void* d_signal, int sig_d
   p.n_tiles = n_tiles;
   p.out = d_out;
   p.seed = seed;
+  // PDS_STFT_KERNEL=ws opts in to the warp-specialised kernel (A/B runs, tests).  It is not the
+  // default yet: its three bank warps are the bottleneck (profiles/), the phased kernel is faster.
+  const char* force = getenv("PDS_STFT_KERNEL");
+  const bool want_ws = force && force[0] == 'w';
+  if (plan->ws && sig_dtype == PDS_F32 && want_ws) {
+    const int grid = (int)std::min<int64_t>(n_tiles, plan->num_sms);
+    pick_ws<512>(plan->power, plan->row_mode)<<<grid, kWsThreads, plan->ws_smem_bytes,
+                                                static_cast<cudaStream_t>(stream)>>>(p);
+    PDS_CUDA_CHECK(cudaGetLastError());
+    return PDS_OK;
+  }
   KernelFn fn = pick_kernel(plan, sig_dtype);
   const int grid = (int)std::min<int64_t>(n_tiles, plan->grid_limit);
   const int threads = plan->fast ? kThreads : kDirectThreads;

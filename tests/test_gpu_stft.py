@@ -161,3 +161,32 @@ def test_host_buffer_entry_point(speech):
         out.ctypes.data, cap, frame_off.ctypes.data_as(i64p), 0))
     for u, sig in enumerate(sigs):
         assert np.array_equal(out[frame_off[u]:frame_off[u + 1]], computer.compute_full(sig))
+
+
+@pytest.mark.parametrize("cfg_name", ["readme", "kaldi", "gammatone_L512", "magnitude"])
+def test_warp_specialised_kernel_matches_phased_and_oracle(speech, monkeypatch, cfg_name):
+    """Both fused kernels (PDS_STFT_KERNEL=ws / phased) on a ragged batch: same features, and
+    within tolerance of the oracle"""
+    cfg = {
+        "readme": cases.README_FBANK,
+        "kaldi": cases.KALDI_FBANK,
+        "gammatone_L512": dict(cases.GAMMATONE_64, frame_length_ms=32),
+        "magnitude": dict(cases.README_FBANK, use_power=False, use_log=False),
+    }[cfg_name]
+    rng = np.random.default_rng(11)
+    computer = build(speech, cfg)
+    lengths = [0, 1, 201, 399, 5000, 16000, 33333, 160 * 32 + 240, 160 * 64 + 241, 160 * 95, 48000] * 3
+    signals = [(rng.standard_normal(n) * 1000).astype(np.float32) for n in lengths]
+    monkeypatch.setenv("PDS_STFT_KERNEL", "ws")
+    ws = computer.compute_batch(signals)
+    monkeypatch.setenv("PDS_STFT_KERNEL", "phased")
+    phased = computer.compute_batch(signals)
+    for sig, a, b in zip(signals, ws, phased):
+        want = oracle_feats(computer, sig.astype(np.float64))
+        assert a.shape == want.shape == b.shape
+        if len(want):
+            assert np.allclose(a, b, rtol=2e-6, atol=2e-6)  # same math, different FMA contraction
+            if computer._log:
+                assert np.abs(a - want).max() <= LOG_TOL
+            else:
+                check_linear(a.astype(np.float64), want)
