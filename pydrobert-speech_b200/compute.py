@@ -247,6 +247,58 @@ class ShortTimeFourierTransformFrameComputer(LinearFilterBankFrameComputer):
         self._reset_stream()
         super().__init__(bank, include_energy=include_energy)
 
+    @classmethod
+    def from_tables(
+        cls,
+        offsets: Sequence[int],
+        truncated_filts: Sequence[np.ndarray],
+        frame_length: int,
+        frame_shift: int,
+        frame_style: str = "centered",
+        window: Optional[np.ndarray] = None,
+        dft_size: Optional[int] = None,
+        use_log: bool = True,
+        use_power: bool = False,
+        include_energy: bool = False,
+        kaldi_shift: bool = False,
+        is_real: bool = False,
+        sampling_rate: float = 16000,
+    ) -> "ShortTimeFourierTransformFrameComputer":
+        """Build a computer straight from ``(offset, truncated response)`` tables and geometry in
+        samples, without a bank object (what the reference's PyTorch module is constructed from,
+        ``torch.py:318-366``)"""
+        if frame_style not in ("centered", "causal"):
+            raise ValueError('Invalid frame style: "{}"'.format(frame_style))
+        self = cls.__new__(cls)
+        self._bank = None
+        self._num_filts = len(offsets)
+        self._include_energy = bool(include_energy)
+        self._rate = sampling_rate
+        self._frame_shift = int(frame_shift)
+        self._frame_length = int(frame_length)
+        self._log, self._power, self._real = bool(use_log), bool(use_power), bool(is_real)
+        self._kaldi_shift = bool(kaldi_shift)
+        self._frame_style = frame_style
+        self._window = (
+            np.ones(self._frame_length) if window is None else np.asarray(window, dtype=np.float64)
+        )
+        if dft_size is None:
+            dft_size = int(2 ** np.ceil(np.log2(self._frame_length)))
+        self._dft_size = int(dft_size)
+        self._filt_start_idxs = [int(o) for o in offsets]
+        self._truncated_filts = [np.asarray(f) for f in truncated_filts]
+        self._weights = fold_filters(
+            self._filt_start_idxs, self._truncated_filts, self._dft_size, self._power, self._real
+        )
+        self._plans = dict()
+        self._reset_stream()
+        return self
+
+    @property
+    def num_coeffs(self) -> int:
+        filts = self._bank.num_filts if self._bank is not None else self._num_filts
+        return filts + int(self._include_energy)
+
     # ---- reference properties ---------------------------------------------------------
     @property
     def frame_style(self) -> str:
@@ -312,7 +364,7 @@ class ShortTimeFourierTransformFrameComputer(LinearFilterBankFrameComputer):
             frame_shift=self._frame_shift,
             dft_size=self._dft_size,
             pad_left=self.pad_left,
-            num_filts=self._bank.num_filts,
+            num_filts=len(self._filt_start_idxs),
             include_energy=int(self._include_energy),
             use_power=int(bool(self._power)),
             use_log=int(bool(self._log)),

@@ -203,8 +203,12 @@ class FeaturePipeline:
         return out, frame_off
 
     def __call__(self, signals: Sequence[np.ndarray]) -> List[np.ndarray]:
+        return self.run_list(signals)
+
+    def run_list(self, signals: Sequence[np.ndarray], utt_base: int = 0) -> List[np.ndarray]:
         """List of 1-D arrays in, list of ``(T, C)`` float32 arrays out (host post-processors,
-        if any, are applied per utterance and may change ``T`` or ``C``)"""
+        if any, are applied per utterance and may change ``T`` or ``C``).  ``utt_base`` is the
+        global index of the first utterance; it keys the dither stream."""
         signals = [np.asarray(s) for s in signals]
         is_stft = isinstance(self.computer, ShortTimeFourierTransformFrameComputer)
         if self._host_pre:
@@ -213,11 +217,12 @@ class FeaturePipeline:
         dtype = np.int16 if (all_pcm and is_stft) else np.float32
         lead = self.computer.pad_left % 4 if is_stft else 0
         packed = PackedSignals.pack(signals, dtype, lead)
-        saved, self._host_pre = self._host_pre, []
+        saved = self._host_pre, self._host_post
+        self._host_pre, self._host_post = [], []
         try:
-            feats, frame_off = self.run_host(packed)
+            feats, frame_off = self.run_host(packed, utt_base=utt_base)
         finally:
-            self._host_pre = saved
+            self._host_pre, self._host_post = saved
         per_utt = [feats[frame_off[u] : frame_off[u + 1]] for u in range(len(signals))]
         for p in self._host_post:
             per_utt = [p.apply(f) if len(f) else f for f in per_utt]

@@ -1,0 +1,189 @@
+"""The PyTorch modules and the signals-to-torch-feat-dir command, mirroring the reference's
+tests/test_torch.py and tests/test_command_line.py:89-179 (which pass unmodified semantics)."""
+import json
+import os
+import wave
+
+import numpy as np
+import pytest
+
+import cases
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def build(speech, cfg):
+    return speech.alias_factory_subclass_from_arg(speech.compute.FrameComputer, cfg)
+
+
+@pytest.mark.parametrize("include_energy", [True, False])
+def test_pytorch_stft_frame_computer(speech, include_energy):
+    import torch
+
+    from pydrobert_speech_b200.torch import PyTorchSTFTFrameComputer, pytorch_stft_frame_computer
+
+    torch.manual_seed(1)
+    signal = torch.randn(16000)
+    cfg = dict(cases.KALDI_FBANK, include_energy=include_energy)
+    computer = build(speech, cfg)
+    module = PyTorchSTFTFrameComputer.from_stft_frame_computer(computer)
+    exp = computer.compute_full(signal.numpy())
+    act = module(signal)
+    assert act.device.type == "cpu" and act.dtype == torch.float32
+    assert np.allclose(exp, act.numpy(), atol=1e-5)
+    on_gpu = module(signal.cuda().double())
+    assert on_gpu.is_cuda and on_gpu.dtype == torch.float64
+    assert np.allclose(exp, on_gpu.cpu().numpy(), atol=1e-5)
+    # built from explicit tables (float32 / complex64 like the reference's from_* default)
+    rebuilt = PyTorchSTFTFrameComputer(
+        list(zip(module.offsets, module.filters)), module.frame_length, module.frame_shift, "centered",
+        module.window, module.dft_size, module.use_log, module.use_power, module.include_energy,
+        module.kaldi_shift, module.is_real)
+    assert np.allclose(exp, rebuilt(signal).numpy(), atol=1e-4)
+    func = pytorch_stft_frame_computer(
+        signal, module.filters, list(module.offsets), module.frame_length, module.frame_shift, True,
+        module.window, module.dft_size, module.use_log, module.use_power, module.include_energy,
+        module.kaldi_shift, module.is_real)
+    assert np.allclose(exp, func.numpy(), atol=1e-4)
+    assert module(torch.zeros(10)).shape == (0, computer.num_coeffs)
+    with pytest.raises(RuntimeError, match="1-dimensional"):
+        module(torch.zeros(3, 100))
+    with pytest.raises(ValueError, match="dft_size"):
+        PyTorchSTFTFrameComputer([(0, torch.ones(3))], 400, 160, dft_size=256)
+
+
+def test_pytorch_pre_and_post(speech):
+    import torch
+
+    from pydrobert_speech_b200 import torch as pt
+
+    torch.manual_seed(2)
+    dither = pt.PyTorchDither.from_dither(speech.pre.Dither(2.0))
+    noisy = dither(torch.zeros(1_000_000))
+    assert torch.isclose(noisy.mean(), torch.tensor(0.0), atol=1e-2)
+    assert torch.isclose(noisy.std(), torch.tensor(2.0), atol=1e-2)
+    torch.manual_seed(2)
+    assert torch.equal(noisy, dither(torch.zeros(1_000_000)))
+    signal = torch.randn(1000, dtype=torch.float64)
+    emph = pt.PyTorchPreemphasize.from_preemphasize(speech.pre.Preemphasize(0.9))(signal)
+    assert np.allclose(emph.numpy(), oracle.preemphasize(signal.numpy(), 0.9), atol=1e-5)
+    feats = torch.randn(50, 8)
+    wrapped = pt.PyTorchPostProcessorWrapper.from_postprocessor(speech.post.Deltas(2))(feats)
+    assert wrapped.shape == (50, 24)
+    assert np.allclose(wrapped.numpy(), speech.post.Deltas(2).apply(feats.numpy()), atol=1e-6)
+    si = build(speech, cases.SI_CASES["si_gabor_energy_power"][0])
+    module = pt.PyTorchSIFrameComputer.from_si_frame_computer(si)
+    sig = torch.randn(3000)
+    assert np.allclose(module(sig).numpy(), si.compute_full(sig.numpy()), atol=1e-5)
+    with pytest.raises(NotImplementedError):
+        module.state_dict()
+
+
+def test_signals_to_torch_feat_dir(speech, tmp_path):
+    import torch
+
+    from pydrobert_speech_b200 import command_line
+
+    torch.manual_seed(50)
+    feat_dir, raw_dir = str(tmp_path / "feat"), str(tmp_path / "raw")
+    map_path, manifest_path = str(tmp_path / "map"), str(tmp_path / "manifest.txt")
+    computer_path, pre_path = str(tmp_path / "fbank.json"), str(tmp_path / "pre.json")
+    with open(computer_path, "w") as f:
+        json.dump(cases.KALDI_FBANK, f)
+    with open(pre_path, "w") as f:
+        f.write('["dither"]\n')
+    os.makedirs(raw_dir)
+    num_utts, utt2signal, utt_ids = 100, dict(), []
+    with open(map_path, "w") as mp:
+        for idx in range(num_utts):
+            utt_id = "utt{:03d}".format(idx)
+            utt_ids.append(utt_id)
+            n = torch.randint(1, 1600, (1,)).item()
+            signal = torch.randint(-(2 ** 15), 2 ** 15 - 1, (n,), dtype=torch.float32)
+            utt2signal[utt_id] = signal
+            kind = idx % 3
+            if kind == 2:
+                path = os.path.join(raw_dir, f"{idx}.wav")
+                with wave.open(path, "wb") as wv:
+                    wv.setnchannels(1)
+                    wv.setsampwidth(2)
+                    wv.setframerate(16000)
+                    wv.writeframes(signal.to(torch.int16).numpy().tobytes())
+            elif kind == 1:
+                path = os.path.join(raw_dir, f"{idx}.npy")
+                np.save(path, signal.numpy())
+            else:
+                path = os.path.join(raw_dir, f"{idx}.pt")
+                torch.save(signal, path)
+            mp.write(f"{utt_id} {path}\n")
+    args = [map_path, computer_path, feat_dir]
+    assert not command_line.signals_to_torch_feat_dir(args)
+    computer = build(speech, cases.KALDI_FBANK)
+    for utt_id in utt_ids:
+        feat = torch.load(os.path.join(feat_dir, f"{utt_id}.pt"))
+        assert feat.dtype == torch.float32 and feat.shape[-1] == 40
+        want = computer.compute_full(utt2signal[utt_id].numpy())
+        assert feat.shape == want.shape and np.allclose(feat.numpy(), want, atol=1e-5)
+    # a small batch size must not change anything
+    assert not command_line.signals_to_torch_feat_dir(args + ["--batch-samples=3000", "--num-workers=3"])
+    for utt_id in utt_ids[::7]:
+        feat = torch.load(os.path.join(feat_dir, f"{utt_id}.pt"))
+        assert np.allclose(feat.numpy(), computer.compute_full(utt2signal[utt_id].numpy()), atol=1e-5)
+    args.pop(1)  # no computer: store the raw audio as (S, 1)
+    assert not command_line.signals_to_torch_feat_dir(args)
+    for utt_id, exp in utt2signal.items():
+        act = torch.load(os.path.join(feat_dir, f"{utt_id}.pt"))
+        assert act.shape == (len(exp), 1) and torch.allclose(exp, act.flatten())
+    args += ["--seed=1", f"--preprocess={pre_path}"]
+    assert not command_line.signals_to_torch_feat_dir(args)
+    for utt_id in utt_ids:
+        noisy = torch.load(os.path.join(feat_dir, f"{utt_id}.pt"))
+        assert not torch.allclose(utt2signal[utt_id], noisy.flatten())
+        utt2signal[utt_id] = noisy
+    args += ["--num-workers=2", f"--manifest={manifest_path}"]
+    assert not command_line.signals_to_torch_feat_dir(args)  # same seed: same noise
+    for utt_id, exp in utt2signal.items():
+        assert torch.allclose(exp, torch.load(os.path.join(feat_dir, f"{utt_id}.pt")))
+    with open(manifest_path) as f:
+        utts = [x.strip() for x in f]
+    assert sorted(utts) == sorted(utt2signal)
+    # utterances already in the manifest are not recomputed, missing ones are
+    utt1, utt2 = utts[:2]
+    exp1, exp2 = utt2signal[utt1], torch.randn_like(utt2signal[utt1])
+    torch.save(exp2, os.path.join(feat_dir, f"{utt1}.pt"))
+    torch.save(exp2, os.path.join(feat_dir, f"{utt2}.pt"))
+    with open(manifest_path, "w") as f:
+        f.write("\n".join(utts[1:]) + "\n")
+    assert not command_line.signals_to_torch_feat_dir(args)
+    assert torch.allclose(exp1, torch.load(os.path.join(feat_dir, f"{utt1}.pt")))
+    assert torch.allclose(exp2, torch.load(os.path.join(feat_dir, f"{utt2}.pt")))
+
+
+def test_cli_fused_preprocessing_and_postprocessing(speech, tmp_path):
+    """dither + preemphasis fused into the kernel, Deltas applied with the CLI's axis=-1"""
+    import torch
+
+    from pydrobert_speech_b200 import command_line
+
+    rng = np.random.default_rng(3)
+    feat_dir, map_path = str(tmp_path / "feat"), str(tmp_path / "map")
+    signals = {f"u{i}": (rng.standard_normal(n) * 300).astype(np.float32) for i, n in enumerate((4000, 9000, 250))}
+    with open(map_path, "w") as mp:
+        for utt, sig in signals.items():
+            np.save(str(tmp_path / f"{utt}.npy"), sig)
+            mp.write(f"{utt} {tmp_path / (utt + '.npy')}\n")
+    args = [map_path, json.dumps(cases.README_FBANK), feat_dir, "--seed=5",
+            '--preprocess=[{"name": "preemph", "coeff": 0.95}]', '--postprocess=[{"name": "deltas", "num_deltas": 1}]']
+    assert command_line.main(["signals-to-torch-feat-dir"] + args) == 0
+    computer = build(speech, cases.README_FBANK)
+    for utt, sig in signals.items():
+        feat = torch.load(os.path.join(feat_dir, f"{utt}.pt")).numpy()
+        base = oracle.stft_features(
+            oracle.preemphasize(sig, 0.95), computer._window, 512, computer._filt_start_idxs,
+            computer._truncated_filts, 160, 199, True, True, True, True)
+        want = np.concatenate([base, oracle.deltas(base.T, 1)[:, base.shape[0]:].T], axis=1)
+        assert feat.shape == want.shape == (computer.num_frames(len(sig)), 82)
+        assert np.abs(feat - want).max() <= 1e-3
+    assert command_line.main(["nonsense"]) == 2
+    assert command_line.signals_to_torch_feat_dir(["--help"]) == 0
