@@ -121,34 +121,51 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
       : "memory");
 }
 
-// Can this tile's span be fetched by a single TMA bulk copy?  (uniform across the CTA)
+// Which part [a0, a1) of a tile's span can be fetched by a TMA bulk copy?  (uniform across the CTA)
+// Interior tiles: all of it.  Utterance-edge tiles: the in-range middle, because the packing puts
+// sample `start` of every tile on a 16-byte grid, so shared-memory index and global index are
+// congruent mod 4; only the reflected ends are filled by hand.  int16 input or fused
+// pre-processing: nothing (a0 == a1).
 template <typename T>
-__device__ __forceinline__ bool tile_is_bulk(const StftParams& p, const pds_tile& tile, int span) {
-  if (sizeof(T) != 4 || p.dither != 0.f || p.preemph != 0.f) return false;
+__device__ __forceinline__ void bulk_range(const StftParams& p, const pds_tile& tile, int span, int& a0,
+                                           int& a1) {
+  a0 = a1 = 0;
+  if (sizeof(T) != 4 || p.dither != 0.f || p.preemph != 0.f) return;
   const long long first = tile.start;
-  if (first < 0 || first + span > (long long)tile.sig_len || (span & 3)) return false;
   const T* src = static_cast<const T*>(p.sig) + tile.sig_off + first;
-  return (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+  if ((reinterpret_cast<uintptr_t>(src) & 15u) != 0) return;
+  const int r0 = (int)max(0LL, -first);
+  const int r1 = (int)min((long long)span, (long long)tile.sig_len - first);
+  const int b0 = (r0 + 3) & ~3, b1 = r1 & ~3;
+  if (b1 - b0 >= 64) a0 = b0, a1 = b1;
 }
 
-// Cooperative per-element staging: reflection at the edges, dtype conversion, fused pre-processing
+// Cooperative per-element staging of [0, a0) and [a1, span): reflection at the edges, dtype
+// conversion, fused pre-processing
 template <typename T, int THREADS>
 __device__ __forceinline__ void stage_samples_slow(float* __restrict__ s_x, const StftParams& p,
-                                                   const pds_tile& tile, int span) {
+                                                   const pds_tile& tile, int span, int a0, int a1) {
   const T* __restrict__ sig = static_cast<const T*>(p.sig);
   const long long first = tile.start;
-  int i = threadIdx.x;
-  for (; i + 3 * THREADS < span; i += 4 * THREADS) {  // four independent loads in flight
+  const int skip = a1 - a0;       // elements covered by the bulk copy
+  const int todo = span - skip;   // element e of the hand-filled part sits at e (e < a0) or e + skip
+  int e = threadIdx.x;
+  for (; e + 3 * THREADS < todo; e += 4 * THREADS) {  // four independent loads in flight
     float v[4];
+    int at[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      v[u] = preprocessed_sample(sig, tile.sig_off, reflect_index(first + i + u * THREADS, tile.sig_len), p,
-                                 tile.utt);
+    for (int u = 0; u < 4; ++u) {
+      const int q = e + u * THREADS;
+      at[u] = q < a0 ? q : q + skip;
+      v[u] = preprocessed_sample(sig, tile.sig_off, reflect_index(first + at[u], tile.sig_len), p, tile.utt);
+    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) s_x[i + u * THREADS] = v[u];
+    for (int u = 0; u < 4; ++u) s_x[at[u]] = v[u];
   }
-  for (; i < span; i += THREADS)
-    s_x[i] = preprocessed_sample(sig, tile.sig_off, reflect_index(first + i, tile.sig_len), p, tile.utt);
+  for (; e < todo; e += THREADS) {
+    const int at = e < a0 ? e : e + skip;
+    s_x[at] = preprocessed_sample(sig, tile.sig_off, reflect_index(first + at, tile.sig_len), p, tile.utt);
+  }
 }
 
 // natural log of a positive, normal float: one MUFU.LG2 and one FMUL.  The argument has already
@@ -416,15 +433,16 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
   if (tile_idx < p.n_tiles) {
     tile = p.tiles[tile_idx];
     const int span = (tile.nframes - 1) * p.S + p.L;
-    pending_bulk = tile_is_bulk<T>(p, tile, span);
-    if (pending_bulk) {
-      if (tid == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // zero-fill above -> async proxy
-        mbar_expect_tx(s_bar, span * 4);
-        bulk_copy_g2s(s_x, static_cast<const T*>(p.sig) + tile.sig_off + tile.start, span * 4, s_bar);
-      }
-    } else {
-      stage_samples_slow<T, kThreads>(s_x, p, tile, span);
+    int a0, a1;
+    bulk_range<T>(p, tile, span, a0, a1);
+    pending_bulk = a1 > a0;
+    if (pending_bulk && tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // zero-fill above -> async proxy
+      mbar_expect_tx(s_bar, (a1 - a0) * 4);
+      bulk_copy_g2s(s_x + a0, static_cast<const T*>(p.sig) + tile.sig_off + tile.start + a0, (a1 - a0) * 4, s_bar);
+    }
+    if (a1 - a0 < span) {
+      stage_samples_slow<T, kThreads>(s_x, p, tile, span, a0, a1);
       __syncthreads();
     }
   }
@@ -453,24 +471,26 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
     // ---- prefetch the next tile's samples while this tile goes through bank + store ----
     const pds_tile cur = tile;
     bool next_slow = false;
-    int next_span = 0;
+    int next_span = 0, a0 = 0, a1 = 0;
     pending_bulk = false;
     if (next_idx < p.n_tiles) {
       tile = next_tile;
       next_span = (tile.nframes - 1) * p.S + p.L;
-      pending_bulk = tile_is_bulk<T>(p, tile, next_span);
-      next_slow = !pending_bulk;
+      bulk_range<T>(p, tile, next_span, a0, a1);
+      pending_bulk = a1 > a0;
+      next_slow = a1 - a0 < next_span;
       if (pending_bulk && tid == 0) {
         // order the generic-proxy reads of s_x above before the async-proxy write
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(s_bar, next_span * 4);
-        bulk_copy_g2s(s_x, static_cast<const T*>(p.sig) + tile.sig_off + tile.start, next_span * 4, s_bar);
+        mbar_expect_tx(s_bar, (a1 - a0) * 4);
+        bulk_copy_g2s(s_x + a0, static_cast<const T*>(p.sig) + tile.sig_off + tile.start + a0, (a1 - a0) * 4,
+                      s_bar);
       }
     }
 
     // ---- filter bank + log -------------------------------------------------------------
     bank_pairs<kThreads / 32, TS>(tid >> 5, tid & 31, s_P, s_e, s_out, bank_weights, s_desc, p, POWER);
-    if (next_slow) stage_samples_slow<T, kThreads>(s_x, p, tile, next_span);
+    if (next_slow) stage_samples_slow<T, kThreads>(s_x, p, tile, next_span, a0, a1);
     __syncthreads();
 
     // ---- coalesced store ---------------------------------------------------------------
@@ -483,24 +503,27 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
 }
 
 // ------------------------------------------------------------------------------------------
-// warp-specialised variant (one CTA per SM, no CTA-wide barriers in steady state)
+// software-pipelined variant (one CTA per SM, no CTA-wide barriers in steady state)
 //
-//   warps 0..15  fft     : each half-warp owns one frame of every 32-frame tile
-//   warps 16..18 bank    : filter-bank contraction + log + coalesced store of the finished tile
-//   warp  19     producer: TMA bulk copies of the sample spans (cooperative copy at utterance edges)
+//   warps 0..15  compute : every iteration  A) fft of this warp's two frames of tile i
+//                                           B) its share of the filter bank of tile i-1
+//   warp  16     producer: TMA bulk copies of the sample spans, two tiles ahead (the in-range
+//                          middle of utterance-edge tiles included; only the reflected ends are
+//                          filled by hand)
+//   warps 17..19 store   : coalesced global store of finished tiles
 //
-// The three roles are coupled only through mbarriers:
-//   x_full[s] / x_empty[s]  sample ring, 2 stages      producer -> fft -> producer
-//   p_full[s] / p_empty[s]  power-spectrum ring, 2 st. fft -> bank -> fft
-// so samples for tile i+1 stream in and tile i-1 goes through the filter bank while the fft warps
-// work on tile i.  Registers are re-balanced with setmaxnreg: the kernel launches with 96 per thread,
-// the bank/producer warpgroup drops to 64 and the 4096 registers it releases into the CTA pool are
-// exactly what the four fft warpgroups need to grow to 104.
+// Stages are handed over through mbarriers only (sample ring x_full/x_empty, power-spectrum ring
+// p_full/p_empty, output ring o_full/o_empty), so step B always finds its input completed an
+// iteration earlier and never stalls; the single tight hand-over is p_empty (the fft of tile i+1
+// re-uses the P stage that the bank step of tile i-1 read).  Compared with the phased kernel this
+// removes both __syncthreads per tile and the exposed staging / store phases.  setmaxnreg moves
+// 4096 registers from the producer/store warpgroup (96 -> 64) to the compute warpgroups (96 -> 104).
 // Used for float32 input without fused pre-processing and G = R1 = 16 (N = 512).
 // ------------------------------------------------------------------------------------------
-constexpr int kWsFftWarps = 16;
-constexpr int kWsBankWarps = 3;
-constexpr int kWsThreads = 32 * (kWsFftWarps + kWsBankWarps + 1);
+constexpr int kWsComputeWarps = 16;
+constexpr int kWsStoreWarps = 3;
+constexpr int kWsThreads = 32 * (kWsComputeWarps + 1 + kWsStoreWarps);
+constexpr int kWsOutStages = 3;
 
 struct WsLayout {
   int x, xstride, w, scr, P, pstride, e, out, bar, desc, wt, total;  // floats; total in bytes
@@ -513,12 +536,12 @@ __host__ __device__ inline WsLayout ws_layout(int N, int G, int R1, int span_max
   s.xstride = (span_max + N + 3) & ~3;
   s.x = take_floats(o, 2 * s.xstride);
   s.w = take_floats(o, N);
-  s.scr = take_floats(o, 2 * (2 * kWsFftWarps) * G * (R1 + 1));
+  s.scr = take_floats(o, 2 * (2 * kWsComputeWarps) * G * (R1 + 1));
   s.pstride = (p_rows * kTileStride + 3) & ~3;
   s.P = take_floats(o, 2 * s.pstride);
   s.e = take_floats(o, 2 * kTileFrames);
-  s.out = take_floats(o, 2 * kTileFrames * C);
-  s.bar = take_floats(o, 16);
+  s.out = take_floats(o, kWsOutStages * kTileFrames * C);
+  s.bar = take_floats(o, 32);
   s.desc = take_floats(o, 4 * npairs);
   s.wt = take_floats(o, weights_floats);
   s.total = o * 4;
@@ -533,9 +556,10 @@ template <int N, bool POWER, int MODE>
 __global__ void __launch_bounds__(kWsThreads, 1) stft_ws_kernel(const __grid_constant__ StftParams p) {
   using Geo = FftGeom<N>;
   constexpr int NC = Geo::NC, G = Geo::G, R1 = Geo::R1;
-  static_assert(G == 16 && R1 == 16, "the warp-specialised kernel maps one frame to each half-warp");
+  static_assert(G == 16 && R1 == 16, "the pipelined kernel maps one frame to each half-warp");
   constexpr int K = NC + 1;
   constexpr int TS = kTileStride;
+  constexpr int NW = kWsComputeWarps;
 
   extern __shared__ __align__(16) float smem[];
   const WsLayout lay = ws_layout(N, G, R1, p.span_max, p.p_rows, p.npairs, p.C, p.weights_total);
@@ -550,6 +574,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) stft_ws_kernel(const __grid_con
   uint64_t* x_empty = bars + 2;  // [2]
   uint64_t* p_full = bars + 4;   // [2]
   uint64_t* p_empty = bars + 6;  // [2]
+  uint64_t* o_full = bars + 8;   // [3]
+  uint64_t* o_empty = bars + 11; // [3]
   int4* s_desc = reinterpret_cast<int4*>(smem + lay.desc);
   float* s_wt = smem + lay.wt;
 
@@ -565,18 +591,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) stft_ws_kernel(const __grid_con
   if (tid == 0) {
     for (int st = 0; st < 2; ++st) {
       mbar_init(&x_full[st], 1);
-      mbar_init(&x_empty[st], kWsFftWarps);
-      mbar_init(&p_full[st], kWsFftWarps);
-      mbar_init(&p_empty[st], kWsBankWarps);
+      mbar_init(&x_empty[st], NW);
+      mbar_init(&p_full[st], NW);
+      mbar_init(&p_empty[st], NW);
+    }
+    for (int st = 0; st < kWsOutStages; ++st) {
+      mbar_init(&o_full[st], NW);
+      mbar_init(&o_empty[st], kWsStoreWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   const long long first_tile = blockIdx.x, step = gridDim.x;
+  const int n_iter = first_tile < p.n_tiles ? (int)((p.n_tiles - first_tile + step - 1) / step) : 0;
 
-  if (warp < kWsFftWarps) {
-    // =============================== fft warps ==========================================
+  if (warp < NW) {
+    // =============================== compute warps ======================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int l = lane & 15;
     float2 tw_stage[R1], tw_split[R1 / 2];
@@ -588,91 +619,162 @@ __global__ void __launch_bounds__(kWsThreads, 1) stft_ws_kernel(const __grid_con
     const bool last_ok0 = 2 * (G * (ROWS - 1) + l) < p.L;
     const bool last_ok1 = 2 * (G * (ROWS - 1) + l) + 1 < p.L;
     const bool want_energy = p.include_energy != 0;
+    const bool use_log = p.use_log != 0;
+    const float log_floor = p.log_floor;
     float2* scr = s_scr + (2 * warp + (lane >> 4)) * Geo::SCR_FLOAT2;
-    int nframes = first_tile < p.n_tiles ? p.tiles[first_tile].nframes : 0;
-    int it = 0;
-    for (long long tile_idx = first_tile; tile_idx < p.n_tiles; tile_idx += step, ++it) {
-      const int stage = it & 1;
-      const uint32_t phase = (it >> 1) & 1;
-      const int next_nframes = tile_idx + step < p.n_tiles ? p.tiles[tile_idx + step].nframes : 0;
-      mbar_wait(&x_full[stage], phase);
-      if (2 * warp < nframes) {
-        mbar_wait(&p_empty[stage], phase ^ 1);  // the bank warps are done with tile it-2
-        const int t = min(2 * warp + (lane >> 4), nframes - 1);
-        fft_frame<N, POWER, MODE>(s_x + stage * lay.xstride + t * p.S, s_w, scr,
-                                  s_P + stage * lay.pstride + t, s_e + stage * kTileFrames + t, tw_stage,
-                                  tw_split, l, last_ok0, last_ok1, want_energy, p);
+
+    // frame count of tile `it`; the next descriptor is fetched an iteration ahead so that its
+    // latency never sits on the critical path
+    int nf0 = 0;
+    int nf_next = n_iter > 0 ? p.tiles[first_tile].nframes : 0;
+
+    for (int it = 0; it < n_iter + 1; ++it) {
+      nf0 = nf_next;
+      if (it + 1 < n_iter) nf_next = p.tiles[first_tile + (long long)(it + 1) * step].nframes;
+      // ---- A: fft of tile `it` ---------------------------------------------------------
+      if (it < n_iter) {
+        const int stage = it & 1;
+        const uint32_t phase = (it >> 1) & 1;
+        mbar_wait(&x_full[stage], phase);
+        if (2 * warp < nf0) {
+          mbar_wait(&p_empty[stage], phase ^ 1);  // every warp is done with the bank step of tile it-2
+          const int t = min(2 * warp + (lane >> 4), nf0 - 1);
+          fft_frame<N, POWER, MODE>(s_x + stage * lay.xstride + t * p.S, s_w, scr,
+                                    s_P + stage * lay.pstride + t, s_e + stage * kTileFrames + t, tw_stage,
+                                    tw_split, l, last_ok0, last_ok1, want_energy, p);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&p_full[stage]);
+          mbar_arrive(&x_empty[stage]);
+        }
       }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&p_full[stage]);
-        mbar_arrive(&x_empty[stage]);
+      // ---- B: this warp's filter pairs of tile `it - 1` --------------------------------
+      if (it >= 1 && it - 1 < n_iter) {
+        const int j = it - 1, stage = j & 1, ostage = j % kWsOutStages;
+        mbar_wait(&p_full[stage], (j >> 1) & 1);
+        mbar_wait(&o_empty[ostage], ((j / kWsOutStages) & 1) ^ 1);  // the store of tile j-3 has drained
+        const float* P = s_P + stage * lay.pstride;
+        float* out = s_out + ostage * kTileFrames * p.C;
+        float* __restrict__ out_row = out + lane * p.C + p.include_energy;
+        // rotate the pair -> warp assignment from tile to tile so that the uneven split
+        // (npairs is rarely a multiple of 16) averages out
+        const int first = (warp + NW - (j % NW)) % NW;
+        for (int pi = first; pi < p.npairs; pi += NW) {
+          const int4 d = s_desc[pi];
+          const float4* __restrict__ wt = reinterpret_cast<const float4*>(s_wt + d.w);
+          const float* __restrict__ pa = P + d.x + lane;
+          const float* __restrict__ pb = P + d.y + lane;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll 1
+          for (int g = 0; g < d.z; ++g) {
+            const float4 wa0 = wt[0], wa1 = wt[1], wb0 = wt[2], wb1 = wt[3];
+            const float x0 = pa[0], x1 = pa[TS], x2 = pa[2 * TS], x3 = pa[3 * TS];
+            const float x4 = pa[4 * TS], x5 = pa[5 * TS], x6 = pa[6 * TS], x7 = pa[7 * TS];
+            const float y0 = pb[0], y1 = pb[TS], y2 = pb[2 * TS], y3 = pb[3 * TS];
+            const float y4 = pb[4 * TS], y5 = pb[5 * TS], y6 = pb[6 * TS], y7 = pb[7 * TS];
+            a0 = fmaf(x0, wa0.x, a0);
+            a1 = fmaf(x1, wa0.y, a1);
+            a2 = fmaf(x2, wa0.z, a2);
+            a3 = fmaf(x3, wa0.w, a3);
+            b0 = fmaf(y0, wb0.x, b0);
+            b1 = fmaf(y1, wb0.y, b1);
+            b2 = fmaf(y2, wb0.z, b2);
+            b3 = fmaf(y3, wb0.w, b3);
+            a0 = fmaf(x4, wa1.x, a0);
+            a1 = fmaf(x5, wa1.y, a1);
+            a2 = fmaf(x6, wa1.z, a2);
+            a3 = fmaf(x7, wa1.w, a3);
+            b0 = fmaf(y4, wb1.x, b0);
+            b1 = fmaf(y5, wb1.y, b1);
+            b2 = fmaf(y6, wb1.z, b2);
+            b3 = fmaf(y7, wb1.w, b3);
+            wt += 4;
+            pa += 8 * TS;
+            pb += 8 * TS;
+          }
+          float va = (a0 + a1) + (a2 + a3), vb = (b0 + b1) + (b2 + b3);
+          if (use_log) {
+            va = fast_log(fmaxf(va, log_floor));
+            vb = fast_log(fmaxf(vb, log_floor));
+          }
+          out_row[2 * pi] = va;
+          if (2 * pi + 1 < p.F) out_row[2 * pi + 1] = vb;
+        }
+        if (want_energy && first == 0) {
+          float v = s_e[stage * kTileFrames + lane] * p.inv_L;
+          if (!POWER) v = sqrtf(v);
+          if (use_log) v = fast_log(fmaxf(v, log_floor));
+          out[lane * p.C] = v;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&p_empty[stage]);
+          mbar_arrive(&o_full[ostage]);
+        }
       }
-      nframes = next_nframes;
     }
   } else {
+    // one setmaxnreg for the whole warpgroup, before its two roles part ways
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (warp < kWsFftWarps + kWsBankWarps) {
-      // ============================= bank warps =========================================
-      const int bw = warp - kWsFftWarps;
-      const int bt = tid - 32 * kWsFftWarps;  // 0..95
-      int it = 0;
-      for (long long tile_idx = first_tile; tile_idx < p.n_tiles; tile_idx += step, ++it) {
-        const int stage = it & 1;
-        const uint32_t phase = (it >> 1) & 1;
-        const pds_tile tile = p.tiles[tile_idx];
-        float* out = s_out + stage * kTileFrames * p.C;
-        mbar_wait(&p_full[stage], phase);
-        bank_pairs<kWsBankWarps, TS>(bw, lane, s_P + stage * lay.pstride, s_e + stage * kTileFrames, out,
-                                     s_wt, s_desc, p, POWER);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_empty[stage]);  // this warp no longer reads the P stage
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kWsBankWarps) : "memory");
-        float* __restrict__ dst = p.out + tile.out_row * p.C;
-        const int total = tile.nframes * p.C;
-        for (int i = bt; i < total; i += 32 * kWsBankWarps) dst[i] = out[i];
-        // out[stage] is rewritten two tiles from now, behind the next tile's bar.sync
+  }
+  if (warp > NW) {
+    // =============================== store warps ========================================
+    const int st = tid - 32 * (NW + 1);  // 0..95
+    for (int j = 0; j < n_iter; ++j) {
+      const int ostage = j % kWsOutStages;
+      const pds_tile tile = p.tiles[first_tile + (long long)j * step];
+      mbar_wait(&o_full[ostage], (j / kWsOutStages) & 1);
+      const float* out = s_out + ostage * kTileFrames * p.C;
+      float* __restrict__ dst = p.out + tile.out_row * p.C;
+      const int total = tile.nframes * p.C;
+      int i = st;
+      for (; i + 3 * 32 * kWsStoreWarps < total; i += 4 * 32 * kWsStoreWarps) {  // four stores in flight
+        const float v0 = out[i], v1 = out[i + 96], v2 = out[i + 192], v3 = out[i + 288];
+        dst[i] = v0, dst[i + 96] = v1, dst[i + 192] = v2, dst[i + 288] = v3;
       }
-    } else {
-      // ============================= producer warp ======================================
-      const float* __restrict__ sig = static_cast<const float*>(p.sig);
-      int it = 0;
-      for (long long tile_idx = first_tile; tile_idx < p.n_tiles; tile_idx += step, ++it) {
-        const int stage = it & 1;
-        const uint32_t phase = (it >> 1) & 1;
-        const pds_tile tile = p.tiles[tile_idx];
-        const int span = (tile.nframes - 1) * p.S + p.L;
-        float* dst = s_x + stage * lay.xstride;
-        const long long first = tile.start;
-        const float* src = sig + tile.sig_off + first;
-        const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
-        const bool bulk = first >= 0 && first + span <= (long long)tile.sig_len && (span & 3) == 0 && aligned;
-        mbar_wait(&x_empty[stage], phase ^ 1);  // the fft warps are done with tile it-2
-        if (bulk) {
-          if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&x_full[stage], span * 4);
-            bulk_copy_g2s(dst, src, span * 4, &x_full[stage]);
-          }
-        } else {
-          // utterance edge: the in-range middle of the span still goes through TMA (when the
-          // packing put it on a 16-byte grid); only the reflected ends are filled by hand
-          const int r0 = (int)max(0LL, -first);
-          const int r1 = (int)min((long long)span, (long long)tile.sig_len - first);
-          int a0 = (r0 + 3) & ~3, a1 = r1 & ~3;
-          if (!aligned || a1 - a0 < 64) a0 = a1 = 0;
-          if (a1 > a0 && lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            bulk_copy_g2s(dst + a0, src + a0, (a1 - a0) * 4, &x_full[stage]);
-          }
-          for (int i = lane; i < a0; i += 32) dst[i] = sig[tile.sig_off + reflect_index(first + i, tile.sig_len)];
-          for (int i = a1 + lane; i < span; i += 32)
-            dst[i] = sig[tile.sig_off + reflect_index(first + i, tile.sig_len)];
-          __syncwarp();
-          if (lane == 0) {
-            if (a1 > a0) mbar_expect_tx(&x_full[stage], (a1 - a0) * 4);  // arrival + the bytes in flight
-            else mbar_arrive(&x_full[stage]);
-          }
+      for (; i < total; i += 32 * kWsStoreWarps) dst[i] = out[i];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[ostage]);
+    }
+  } else if (warp == NW) {
+    // =============================== producer warp ======================================
+    const float* __restrict__ sig = static_cast<const float*>(p.sig);
+    for (int it = 0; it < n_iter; ++it) {
+      const int stage = it & 1;
+      const uint32_t phase = (it >> 1) & 1;
+      const pds_tile tile = p.tiles[first_tile + (long long)it * step];
+      const int span = (tile.nframes - 1) * p.S + p.L;
+      float* dst = s_x + stage * lay.xstride;
+      const long long first = tile.start;
+      const float* src = sig + tile.sig_off + first;
+      const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+      const bool bulk = first >= 0 && first + span <= (long long)tile.sig_len && (span & 3) == 0 && aligned;
+      mbar_wait(&x_empty[stage], phase ^ 1);  // the compute warps are done with tile it-2
+      if (bulk) {
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(&x_full[stage], span * 4);
+          bulk_copy_g2s(dst, src, span * 4, &x_full[stage]);
+        }
+      } else {
+        // utterance edge: the in-range middle of the span still goes through TMA (when the
+        // packing put it on a 16-byte grid); only the reflected ends are filled by hand
+        const int r0 = (int)max(0LL, -first);
+        const int r1 = (int)min((long long)span, (long long)tile.sig_len - first);
+        int a0 = (r0 + 3) & ~3, a1 = r1 & ~3;
+        if (!aligned || a1 - a0 < 64) a0 = a1 = 0;
+        if (a1 > a0 && lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          bulk_copy_g2s(dst + a0, src + a0, (a1 - a0) * 4, &x_full[stage]);
+        }
+        for (int i = lane; i < a0; i += 32) dst[i] = sig[tile.sig_off + reflect_index(first + i, tile.sig_len)];
+        for (int i = a1 + lane; i < span; i += 32)
+          dst[i] = sig[tile.sig_off + reflect_index(first + i, tile.sig_len)];
+        __syncwarp();
+        if (lane == 0) {
+          if (a1 > a0) mbar_expect_tx(&x_full[stage], (a1 - a0) * 4);  // arrival + the bytes in flight
+          else mbar_arrive(&x_full[stage]);
         }
       }
     }
