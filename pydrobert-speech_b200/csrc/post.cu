@@ -17,7 +17,9 @@ namespace pds {
 // ------------------------------------------------------------------------------------------
 constexpr int kDeltaMaxTaps = 240;
 constexpr int kDeltaMaxOrders = 8;
-constexpr int kDeltaRows = 32;  // rows of output per CTA
+constexpr int kDeltaMaxRows = 128;  // rows of output per CTA (fewer when the columns are wide)
+constexpr int kDeltaMaxChunk = 256;  // columns per CTA
+constexpr int kDeltaThreads = 256;
 
 struct DeltaParams {
   const float* in;
@@ -28,57 +30,86 @@ struct DeltaParams {
   int cols;
   int orders;
   int half_max;
+  int rows_per_cta;
+  int chunk;  // columns per CTA
   int filt_off[kDeltaMaxOrders];
   int filt_len[kDeltaMaxOrders];
   float taps[kDeltaMaxTaps];
 };
 
-__global__ void __launch_bounds__(256) deltas_kernel(const __grid_constant__ DeltaParams p) {
-  extern __shared__ __align__(16) float s_rows[];  // (kDeltaRows + 2*half_max) x cols
-  __shared__ long long s_utt_of_first;
+// One CTA produces `rows_per_cta` consecutive rows of one column chunk: the rows plus a halo of
+// half_max rows on either side are staged in shared memory once (coalesced; each input row is read
+// from HBM ~1.06 times), every thread then walks (row, col) pairs with col fastest -- no integer
+// division in the loops -- and clamps the time index to its utterance's range, looked up once per row.
+__global__ void __launch_bounds__(kDeltaThreads) deltas_kernel(const __grid_constant__ DeltaParams p) {
+  extern __shared__ __align__(16) float s_rows[];  // (R + 2*half_max) x cw | lo[R] | hi[R]
   const int tid = threadIdx.x;
-  const long long r0 = (long long)blockIdx.x * kDeltaRows;
-  const int nrows = (int)min((long long)kDeltaRows, p.total_rows - r0);
-  if (tid == 0) {
-    // utterance containing r0: largest u with row_off[u] <= r0 (skipping empty utterances later)
-    long long lo = 0, hi = p.n_utts;
+  const int R = p.rows_per_cta, H = p.half_max, cols = p.cols;
+  const long long r0 = (long long)blockIdx.x * R;
+  const int nrows = (int)min((long long)R, p.total_rows - r0);
+  const int col0 = blockIdx.y * p.chunk;
+  const int cw = min(p.chunk, cols - col0);
+  const int stage_rows = nrows + 2 * H;
+  int* s_lo = reinterpret_cast<int*>(s_rows + (R + 2 * H) * p.chunk);
+  int* s_hi = s_lo + R;
+
+  // utterance bounds of every output row, relative to r0 - H (the first staged row)
+  if (tid < nrows) {
+    const long long r = r0 + tid;
+    long long lo = 0, hi = p.n_utts;  // largest u with row_off[u] <= r (skips empty utterances)
     while (hi - lo > 1) {
       const long long mid = (lo + hi) >> 1;
-      if (p.row_off[mid] <= r0) lo = mid; else hi = mid;
+      if (p.row_off[mid] <= r) lo = mid; else hi = mid;
     }
-    s_utt_of_first = lo;
+    s_lo[tid] = (int)(p.row_off[lo] - (r0 - H));
+    s_hi[tid] = (int)(p.row_off[lo + 1] - 1 - (r0 - H));
+  }
+  // stage the rows (clamped to the matrix; per-utterance clamping happens on use)
+  const int dr = kDeltaThreads / cw, dc = kDeltaThreads - dr * cw;
+  {
+    const long long first = r0 - H;
+    const int total = stage_rows * cw;
+    if (cw == cols && first >= 0 && first + stage_rows <= p.total_rows) {
+      const float* __restrict__ src = p.in + first * cols;  // one contiguous block
+      int i = tid;
+      for (; i + 3 * kDeltaThreads < total; i += 4 * kDeltaThreads) {
+        const float a = src[i], b = src[i + kDeltaThreads], c = src[i + 2 * kDeltaThreads],
+                    d = src[i + 3 * kDeltaThreads];
+        s_rows[i] = a, s_rows[i + kDeltaThreads] = b, s_rows[i + 2 * kDeltaThreads] = c,
+        s_rows[i + 3 * kDeltaThreads] = d;
+      }
+      for (; i < total; i += kDeltaThreads) s_rows[i] = src[i];
+    } else {
+      int sr = tid / cw, c = tid - sr * cw;
+      for (int i = tid; i < total; i += kDeltaThreads) {
+        const long long r = max(0LL, min(p.total_rows - 1, first + sr));
+        s_rows[i] = p.in[r * cols + col0 + c];
+        sr += dr, c += dc;
+        if (c >= cw) c -= cw, ++sr;
+      }
+    }
   }
   __syncthreads();
-  const int H = p.half_max, cols = p.cols;
-  const int stage_rows = nrows + 2 * H;
-  // stage rows r0-H .. r0+nrows+H (clamped to the matrix); per-utterance clamping happens on use
-  for (int i = tid; i < stage_rows * cols; i += blockDim.x) {
-    const int sr = i / cols, c = i - sr * cols;
-    long long r = r0 - H + sr;
-    r = max(0LL, min(p.total_rows - 1, r));
-    s_rows[i] = p.in[r * cols + c];
-  }
-  __syncthreads();
+
   const int out_cols = cols * (p.orders + 1);
-  for (int i = tid; i < nrows * cols; i += blockDim.x) {
-    const int lr = i / cols, c = i - lr * cols;
-    const long long r = r0 + lr;
-    long long u = s_utt_of_first;
-    while (u + 1 < p.n_utts && p.row_off[u + 1] <= r) ++u;  // few steps: tiles rarely span utterances
-    const long long u_lo = p.row_off[u], u_hi = p.row_off[u + 1];
-    float* __restrict__ dst = p.out + r * out_cols + c;
-    dst[0] = s_rows[(lr + H) * cols + c];
+  int lr = tid / cw, c = tid - lr * cw;
+  for (int i = tid; i < nrows * cw; i += kDeltaThreads) {
+    const int lo = s_lo[lr], hi = s_hi[lr];
+    const int centre = lr + H;  // staged index of this row
+    float* __restrict__ dst = p.out + (r0 + lr) * out_cols + col0 + c;
+    dst[0] = s_rows[centre * cw + c];
     for (int k = 0; k < p.orders; ++k) {
       const int len = p.filt_len[k], half = (len - 1) / 2;
-      const float* f = p.taps + p.filt_off[k];
+      const float* __restrict__ f = p.taps + p.filt_off[k];
       float acc = 0.f;
       for (int j = 0; j < len; ++j) {
-        long long rr = r + j - half;
-        rr = max(u_lo, min(u_hi - 1, rr));
-        acc = fmaf(f[j], s_rows[((int)(rr - r0) + H) * cols + c], acc);
+        const int rr = max(lo, min(hi, centre + j - half));
+        acc = fmaf(f[j], s_rows[rr * cw + c], acc);
       }
       dst[(k + 1) * cols] = acc;
     }
+    lr += dr, c += dc;
+    if (c >= cw) c -= cw, ++lr;
   }
 }
 
@@ -220,15 +251,22 @@ extern "C" int pds_deltas(const float* d_in, float* d_out, int64_t total_rows, i
     at += len;
     p.half_max = std::max(p.half_max, (len - 1) / 2);
   }
-  const size_t smem = sizeof(float) * (size_t)(kDeltaRows + 2 * p.half_max) * n_cols;
+  // column chunks of at most 256, and as many rows per CTA as ~64 KB of shared memory hold
+  p.chunk = std::min<int>(n_cols, kDeltaMaxChunk);
+  const int budget_rows = (64 * 1024) / (int)(sizeof(float) * p.chunk) - 2 * p.half_max;
+  p.rows_per_cta = std::max(8, std::min(kDeltaMaxRows, budget_rows));
+  const size_t smem = sizeof(float) * (size_t)(p.rows_per_cta + 2 * p.half_max) * p.chunk +
+                      2 * sizeof(int) * p.rows_per_cta;
   if (smem > 200 * 1024) {
-    set_error("deltas: %d columns x %d context rows exceed shared memory", n_cols, p.half_max);
+    set_error("deltas: a context of %d rows exceeds shared memory", p.half_max);
     return PDS_ERR_UNSUPPORTED;
   }
   if (smem > 48 * 1024)
     PDS_CUDA_CHECK(cudaFuncSetAttribute(deltas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long grid = (total_rows + kDeltaRows - 1) / kDeltaRows;
-  deltas_kernel<<<(unsigned)grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  const long long grid_x = (total_rows + p.rows_per_cta - 1) / p.rows_per_cta;
+  const int grid_y = (n_cols + p.chunk - 1) / p.chunk;
+  PDS_REQUIRE(grid_y <= 65535, "too many columns (%d)", n_cols);
+  deltas_kernel<<<dim3((unsigned)grid_x, (unsigned)grid_y), kDeltaThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
   PDS_CUDA_CHECK(cudaGetLastError());
   return PDS_OK;
 }

@@ -35,20 +35,25 @@ struct SiParams {
   float log_floor;
 };
 
-// y index i of the full convolution reads padded samples i-k; padded index q maps to x[q - pad_left]
+// y index i of the full convolution reads padded samples i-k; padded index q maps to x[q - pad_left].
+// With the taps reversed (g[j] = h[Mp-1-j], Mp = M rounded up to a multiple of 8, zero padded) this
+// is the correlation y[i] = sum_j g[j] * xs[i + j] over the staged span xs.
 template <bool REAL, bool POWER>
 __global__ void __launch_bounds__(kSiThreads, 2) si_direct_kernel(const __grid_constant__ SiParams p) {
   extern __shared__ __align__(16) float smem[];
   const int S = p.S, M = p.M, C = p.C;
-  const int ny_max = (kSiTileFrames + 1) * S;          // pooled samples per tile
-  const int nx_max = ny_max + M - 1 + kSiSamplesPerThread;  // signal span they depend on
-  float* s_x = smem;                                    // [nx_max]
-  float* s_w = s_x + ((nx_max + 3) & ~3);               // [2S]
-  float* s_acc = s_w + ((2 * S + 3) & ~3);              // [kSiTileFrames][C]
-  float2* s_h = reinterpret_cast<float2*>(s_acc + ((kSiTileFrames * C + 3) & ~3));  // [M] taps of one filter per warp
+  const int Mp = (M + 7) & ~7;
+  constexpr int SPT = kSiSamplesPerThread;
+  const int ny_max = (kSiTileFrames + 1) * S;  // pooled samples per tile
+  const int ny_pad = (ny_max + 32 * SPT - 1) / (32 * SPT) * (32 * SPT);
+  const int nx_max = ny_pad + Mp + 8;          // staged samples (idle lanes read in bounds)
+  float* s_x = smem;                           // [nx_max]
+  float* s_w = s_x + ((nx_max + 3) & ~3);      // [2S]
+  float* s_acc = s_w + ((2 * S + 3) & ~3);     // [kSiTileFrames][C]
+  float2* s_h = reinterpret_cast<float2*>(s_acc + ((kSiTileFrames * C + 3) & ~3));  // [warps][Mp] reversed taps
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kSiThreads / 32;
-  float2* my_h = s_h + warp * M;
+  float2* my_h = s_h + warp * Mp;
 
   for (int i = tid; i < 2 * S; i += kSiThreads) s_w[i] = p.window[i];
 
@@ -57,55 +62,62 @@ __global__ void __launch_bounds__(kSiThreads, 2) si_direct_kernel(const __grid_c
     const int nframes = tile.nframes;
     const int ny = (nframes + 1) * S;
     const long long y0 = tile.start;  // first pooled sample (index into the full convolution)
-    const int nx = ny + M - 1;
     __syncthreads();
-    // s_x[j] = padded sample (y0 - (M-1) + j); zero outside the signal
-    for (int j = tid; j < nx + kSiSamplesPerThread; j += kSiThreads) {
-      const long long g = y0 - (M - 1) + j - p.pad_left;
-      s_x[j] = (g >= 0 && g < tile.sig_len && j < nx) ? p.sig[tile.sig_off + g] : 0.f;
+    // xs[j] = padded sample (y0 - (Mp-1) + j); zero outside the signal
+    for (int j = tid; j < nx_max; j += kSiThreads) {
+      const long long g = y0 - (Mp - 1) + j - p.pad_left;
+      s_x[j] = (g >= 0 && g < tile.sig_len) ? p.sig[tile.sig_off + g] : 0.f;
     }
     for (int i = tid; i < kSiTileFrames * C; i += kSiThreads) s_acc[i] = 0.f;
     __syncthreads();
 
     // warp task = (filter c, chunk of 32*SPT consecutive samples)
-    const int chunk = 32 * kSiSamplesPerThread;
+    const int chunk = 32 * SPT;
     const int nchunks = (ny + chunk - 1) / chunk;
     for (int c = warp; c < C; c += NW) {
       __syncwarp();
-      for (int k = lane; k < M; k += 32)
-        my_h[k] = make_float2(p.h_re[c * M + k], REAL ? 0.f : p.h_im[c * M + k]);
+      for (int k = lane; k < Mp; k += 32) {
+        const int src = Mp - 1 - k;  // reversed, zero padded at the front of g
+        my_h[k] = src < M ? make_float2(p.h_re[c * M + src], REAL ? 0.f : p.h_im[c * M + src])
+                          : make_float2(0.f, 0.f);
+      }
       __syncwarp();
       for (int ch = 0; ch < nchunks; ++ch) {
-        const int i0 = ch * chunk + lane * kSiSamplesPerThread;  // first output of this thread
-        // y[i0 + s] = sum_k h[k] * xs[(i0 + s) + (M-1) - k]; slide from k = M-1 down to 0
-        float re[kSiSamplesPerThread], im[kSiSamplesPerThread], xw[kSiSamplesPerThread];
+        const int i0 = ch * chunk + lane * SPT;  // first output of this thread (multiple of 8)
+        float re[SPT], im[SPT], w[2 * SPT];
 #pragma unroll
-        for (int s = 0; s < kSiSamplesPerThread; ++s) re[s] = 0.f, im[s] = 0.f;
-        // window of samples xs[i0 + s + (M-1) - k] for s = 0..SPT-1; start at k = M-1 -> xs[i0 + s]
-        const float* xs = s_x + min(i0, nx);  // clamp keeps idle lanes in bounds
-#pragma unroll
-        for (int s = 0; s < kSiSamplesPerThread; ++s) xw[s] = xs[s];
-        int k = M - 1;
-        int next = kSiSamplesPerThread;  // next sample to shift in: xs[next]
-        for (; k >= 0; --k) {
-          const float2 h = my_h[k];
-#pragma unroll
-          for (int s = 0; s < kSiSamplesPerThread; ++s) {
-            re[s] = fmaf(h.x, xw[s], re[s]);
-            if (!REAL) im[s] = fmaf(h.y, xw[s], im[s]);
-          }
-          // advance: k -> k-1 means every output reads one sample later
-#pragma unroll
-          for (int s = 0; s + 1 < kSiSamplesPerThread; ++s) xw[s] = xw[s + 1];
-          xw[kSiSamplesPerThread - 1] = (i0 + next < nx + kSiSamplesPerThread) ? xs[next] : 0.f;
-          ++next;
+        for (int q = 0; q < SPT; ++q) re[q] = 0.f, im[q] = 0.f;
+        const float4* xs4 = reinterpret_cast<const float4*>(s_x + i0);
+        {
+          const float4 a = xs4[0], b = xs4[1];
+          w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w, w[4] = b.x, w[5] = b.y, w[6] = b.z, w[7] = b.w;
         }
-        // pooling: sample r = i0 + s feeds frame t = r / S (window half 0) and t - 1 (half 1)
+        for (int j0 = 0; j0 < Mp; j0 += 8) {
+          {  // samples j0+8 .. j0+15 of this thread's window
+            const float4 a = xs4[j0 / 4 + 2], b = xs4[j0 / 4 + 3];
+            w[8] = a.x, w[9] = a.y, w[10] = a.z, w[11] = a.w, w[12] = b.x, w[13] = b.y, w[14] = b.z, w[15] = b.w;
+          }
+          const float4* g4 = reinterpret_cast<const float4*>(my_h + j0);  // two taps per float4
 #pragma unroll
-        for (int s = 0; s < kSiSamplesPerThread; ++s) {
-          const int r = i0 + s;
+          for (int jj = 0; jj < 4; ++jj) {
+            const float4 g = g4[jj];
+#pragma unroll
+            for (int q = 0; q < SPT; ++q) {
+              re[q] = fmaf(g.x, w[q + 2 * jj], re[q]);
+              if (!REAL) im[q] = fmaf(g.y, w[q + 2 * jj], im[q]);
+              re[q] = fmaf(g.z, w[q + 2 * jj + 1], re[q]);
+              if (!REAL) im[q] = fmaf(g.w, w[q + 2 * jj + 1], im[q]);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < SPT; ++q) w[q] = w[q + SPT];
+        }
+        // pooling: sample r = i0 + q feeds frame t = r / S (window half 0) and t - 1 (half 1)
+#pragma unroll
+        for (int q = 0; q < SPT; ++q) {
+          const int r = i0 + q;
           if (r < ny) {
-            float u = REAL ? re[s] * re[s] : re[s] * re[s] + im[s] * im[s];
+            float u = REAL ? re[q] * re[q] : re[q] * re[q] + im[q] * im[q];
             if (!POWER) u = sqrtf(u);
             const int t = r / S, n = r - t * S;
             if (t < nframes) atomicAdd(&s_acc[t * C + c], s_w[n] * u);
@@ -188,10 +200,13 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
   p.use_log = d->use_log ? 1 : 0;
   p.log_floor = d->log_floor;
   const int S = plan->S, M = plan->M, C = plan->C;
-  const int ny_max = (kSiTileFrames + 1) * S, nx_max = ny_max + M - 1 + kSiSamplesPerThread;
+  const int Mp = (M + 7) & ~7;
+  const int ny_max = (kSiTileFrames + 1) * S;
+  const int ny_pad = (ny_max + 32 * kSiSamplesPerThread - 1) / (32 * kSiSamplesPerThread) * (32 * kSiSamplesPerThread);
+  const int nx_max = ny_pad + Mp + 8;
   plan->smem_bytes = sizeof(float) * (size_t)(((nx_max + 3) & ~3) + ((2 * S + 3) & ~3) +
                                              ((kSiTileFrames * C + 3) & ~3)) +
-                     sizeof(float2) * (size_t)M * (kSiThreads / 32);
+                     sizeof(float2) * (size_t)Mp * (kSiThreads / 32);
   cudaDeviceProp prop;
   err = cudaGetDeviceProperties(&prop, device);
   if (err != cudaSuccess || plan->smem_bytes > prop.sharedMemPerBlockOptin) {

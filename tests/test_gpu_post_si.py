@@ -46,6 +46,20 @@ def test_deltas_short_and_axes(speech, golden):
     assert np.abs(got[:, 8:16] - want[:, 30:60].T).max() <= 1e-5
 
 
+def test_deltas_wide_and_long(speech):
+    """column chunking (cols > 256) and many row tiles, against the oracle"""
+    rng = np.random.default_rng(7)
+    feats = rng.standard_normal((700, 41))
+    got = speech.post.Deltas(2).apply(feats)  # CLI default: filter along the 41 coefficients, 700 columns
+    want = oracle.deltas(feats.T, 2)
+    assert got.shape == (700, 123)
+    assert np.abs(got[:, 41:82] - want[:, 700:1400].T).max() <= 1e-5
+    assert np.abs(got[:, 82:] - want[:, 1400:].T).max() <= 1e-5
+    tall = rng.standard_normal((5000, 300)).astype(np.float32)
+    got = speech.post.Deltas(3, context_window=3).apply(tall, axis=0)
+    assert np.abs(got - oracle.deltas(tall, 3, 3)).max() <= 1e-4
+
+
 def test_deltas_respect_utterance_boundaries(speech):
     import torch
 
