@@ -19,21 +19,21 @@ static void emulate(const float* frame, int L, const float* window, float* P, in
   const double two_pi = 6.283185307179586476925286766559;
   std::vector<float> win(N, 0.f), x(N, 0.f);
   for (int i = 0; i < L; ++i) win[i] = 0.5f * window[i], x[i] = frame[i];
-  std::vector<float2> scr(Geo::SCR_FLOAT2);
-  std::vector<std::vector<float2>> Z(G, std::vector<float2>(R1));
+  std::vector<cplx> scr(Geo::SCR_FLOAT2);
+  std::vector<std::vector<cplx>> Z(G, std::vector<cplx>(R1));
   const int rows_full = L / (2 * G), row_partial = (L % (2 * G)) != 0;
   for (int l = 0; l < G; ++l) {  // stage 1 of every lane
-    float2 z[R1];
+    cplx z[R1];
     for (int r = 0; r < R1; ++r) {
       if (r < rows_full) {
-        z[r] = make_float2(x[2 * (G * r + l)] * win[2 * (G * r + l)],
-                           x[2 * (G * r + l) + 1] * win[2 * (G * r + l) + 1]);
+        z[r] = cmul2(cmake(x[2 * (G * r + l)], x[2 * (G * r + l) + 1]),
+                     cmake(win[2 * (G * r + l)], win[2 * (G * r + l) + 1]));
       } else if (r == rows_full && row_partial) {
         const int i0 = 2 * (G * r + l);
         const float x0 = i0 < L ? x[i0] : 0.f, x1 = i0 + 1 < L ? x[i0 + 1] : 0.f;
-        z[r] = make_float2(x0 * win[i0], x1 * win[i0 + 1]);
+        z[r] = cmake(x0 * win[i0], x1 * win[i0 + 1]);
       } else {
-        z[r] = make_float2(0.f, 0.f);
+        z[r] = cmake(0.f, 0.f);
       }
     }
     Dft<R1>::run(z);
@@ -45,7 +45,7 @@ static void emulate(const float* frame, int L, const float* window, float* P, in
   }
   for (int l = 0; l < G; ++l) {  // stage 2 of every lane
     for (int j = 0; j < NSUB; ++j) {
-      float2 v[G];
+      cplx v[G];
       for (int n2 = 0; n2 < G; ++n2) v[n2] = scr[n2 * Geo::SCR_STRIDE + l + G * j];
       Dft<G>::run(v);
       for (int k2 = 0; k2 < G; ++k2) Z[l][j + NSUB * k2] = v[k2];
@@ -54,21 +54,21 @@ static void emulate(const float* frame, int L, const float* window, float* P, in
   for (int l = 0; l < G; ++l) {  // split
     const int partner = (G - l) % G;
     for (int m = 0; m < R1 / 2; ++m) {
-      float2 b = Z[partner][R1 - 1 - m];  // the shuffle
+      cplx b = Z[partner][R1 - 1 - m];  // the shuffle
       if (l == 0) b = Z[0][(R1 - m) % R1];
       const double a = -two_pi * (double)(l + G * m) / N;
-      float2 xk, xq;
+      cplx xk, xq;
       split_pair(Z[l][m], b, make_float2((float)std::cos(a), (float)std::sin(a)), xk, xq);
-      float pk = xk.x * xk.x + xk.y * xk.y, pq = xq.x * xq.x + xq.y * xq.y;
+      float pk = cnorm(xk), pq = cnorm(xq);
       if (!power) pk = std::sqrt(pk), pq = std::sqrt(pq);
       const int k = l + G * m;
       P[k] = pk;
       P[NC - k] = pq;
     }
     if (l == 0) {
-      float2 xk, xq;
+      cplx xk, xq;
       split_pair(Z[0][R1 / 2], Z[0][R1 / 2], make_float2(0.f, -1.f), xk, xq);
-      float pk = xk.x * xk.x + xk.y * xk.y;
+      float pk = cnorm(xk);
       if (!power) pk = std::sqrt(pk);
       P[NC / 2] = pk;
     }

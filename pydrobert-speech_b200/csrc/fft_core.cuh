@@ -16,8 +16,18 @@
 // index (R1-m) mod R1 of lane 0 itself).
 #pragma once
 
+// Arithmetic: on the device a complex value is ONE 64-bit register pair and every complex
+// add / sub / multiply-add is a packed FP32x2 instruction (PTX add/sub/mul/fma.rn.f32x2 -> SASS
+// FADD2 / FMUL2 / FFMA2, new on sm_100).  The FMA pipe retires the same number of lanes per clock
+// as with scalar FFMA, but each packed instruction takes one issue slot instead of two, and the
+// half swaps / sign flips a complex multiply needs are folded by ptxas into operand modifiers
+// (R4.F32x2.LO_HI.NP ...), so a twiddle multiply is 2 instructions and a butterfly 2 -- the fft
+// phase is issue-bound, so this is where the time goes (measured: tools/ubench/f32x2.cu).
+// Compiled by g++ (csrc/emu_fft.cpp) the same templates run on plain float pairs.
+#include <cstdint>
+
 #ifdef __CUDACC__
-#define PDS_HD __host__ __device__ __forceinline__
+#define PDS_HD __device__ __forceinline__
 #else
 #define PDS_HD inline
 struct float2 {
@@ -102,44 +112,107 @@ constexpr double kSin32[32] = {
     -0.38268343236508977173,
     -0.19509032201612826785};
 
-PDS_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-PDS_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-PDS_HD float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// ---- the complex value type -----------------------------------------------------------------
+#ifdef __CUDACC__
+struct cplx {
+  unsigned long long v;  // {re (low half), im (high half)}: bit-compatible with float2 in memory
+};
+PDS_HD cplx cmake(float re, float im) {
+  cplx r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(re), "f"(im));
+  return r;
+}
+PDS_HD float cre(cplx a) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+  return lo;
+}
+PDS_HD float cim(cplx a) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+  return hi;
+}
+PDS_HD cplx cadd(cplx a, cplx b) {
+  cplx r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+PDS_HD cplx csub(cplx a, cplx b) {
+  cplx r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+PDS_HD cplx cmul2(cplx a, cplx b) {  // element-wise: (a.re b.re, a.im b.im)
+  cplx r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+PDS_HD cplx cfma2(cplx a, cplx b, cplx c) {  // element-wise a * b + c
+  cplx r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+#else
+struct cplx {
+  float x, y;
+};
+PDS_HD cplx cmake(float re, float im) {
+  cplx r;
+  r.x = re;
+  r.y = im;
+  return r;
+}
+PDS_HD float cre(cplx a) { return a.x; }
+PDS_HD float cim(cplx a) { return a.y; }
+PDS_HD cplx cadd(cplx a, cplx b) { return cmake(a.x + b.x, a.y + b.y); }
+PDS_HD cplx csub(cplx a, cplx b) { return cmake(a.x - b.x, a.y - b.y); }
+PDS_HD cplx cmul2(cplx a, cplx b) { return cmake(a.x * b.x, a.y * b.y); }
+PDS_HD cplx cfma2(cplx a, cplx b, cplx c) { return cmake(a.x * b.x + c.x, a.y * b.y + c.y); }
+#endif
+
+PDS_HD cplx cswap(cplx a) { return cmake(cim(a), cre(a)); }       // folded into an operand modifier
+PDS_HD float2 c2f(cplx a) { return make_float2(cre(a), cim(a)); }
+PDS_HD cplx f2c(float2 a) { return cmake(a.x, a.y); }
+// a * (wr + i wi) = (a.re wr - a.im wi, a.im wr + a.re wi): FMUL2 + FFMA2
+PDS_HD cplx cmul(cplx a, float wr, float wi) {
+  return cfma2(a, cmake(wr, wr), cmul2(cswap(a), cmake(-wi, wi)));
+}
+PDS_HD cplx cmul(cplx a, float2 w) { return cmul(a, w.x, w.y); }
+// e + (-i) o and e - (-i) o, the radix-4 style butterfly with the trivial twiddle -i
+PDS_HD cplx cadd_negi(cplx e, cplx o) { return cfma2(cswap(o), cmake(1.f, -1.f), e); }
+PDS_HD cplx csub_negi(cplx e, cplx o) { return cfma2(cswap(o), cmake(-1.f, 1.f), e); }
+// a + conj(b), a - conj(b)
+PDS_HD cplx cadd_conj(cplx a, cplx b) { return cfma2(b, cmake(1.f, -1.f), a); }
+PDS_HD cplx csub_conj(cplx a, cplx b) { return cfma2(b, cmake(-1.f, 1.f), a); }
+PDS_HD float cnorm(cplx a) {  // |a|^2
+  const cplx sq = cmul2(a, a);
+  return cre(sq) + cim(sq);
 }
 
-// o * W_R^K with the trivial cases resolved at compile time (forward transform: W = e^{-2 pi i/R})
+// One radix-2 butterfly with twiddle W_R^K on the odd input: x_lo = e + W o, x_hi = e - W o
 template <int R, int K>
-PDS_HD float2 mul_twiddle(float2 o) {
+PDS_HD void butterfly(cplx e, cplx o, cplx& x_lo, cplx& x_hi) {
   static_assert(R <= 32 && 32 % R == 0, "radix limited to 32");
   constexpr int idx = (K * (32 / R)) % 32;
   if constexpr (idx == 0) {
-    return o;
-  } else if constexpr (idx == 8) {  // -i
-    return make_float2(o.y, -o.x);
-  } else if constexpr (idx == 16) {  // -1
-    return make_float2(-o.x, -o.y);
-  } else if constexpr (idx == 24) {  // +i
-    return make_float2(-o.y, o.x);
-  } else if constexpr (idx == 4) {  // (1 - i)/sqrt2
-    constexpr float c = (float)kCos32[4];
-    return make_float2(c * (o.x + o.y), c * (o.y - o.x));
-  } else if constexpr (idx == 12) {  // (-1 - i)/sqrt2
-    constexpr float c = (float)kCos32[4];
-    return make_float2(c * (o.y - o.x), -c * (o.x + o.y));
+    x_lo = cadd(e, o);
+    x_hi = csub(e, o);
+  } else if constexpr (idx == 8) {  // W = -i
+    x_lo = cadd_negi(e, o);
+    x_hi = csub_negi(e, o);
   } else {
     constexpr float wr = (float)kCos32[idx];
     constexpr float wi = (float)(-kSin32[idx]);
-    return make_float2(o.x * wr - o.y * wi, o.x * wi + o.y * wr);
+    const cplx t = cmul(o, wr, wi);
+    x_lo = cadd(e, t);
+    x_hi = csub(e, t);
   }
 }
 
 template <int R, int K>
 struct Butterflies {
-  static PDS_HD void run(float2 (&x)[R], const float2 (&e)[R / 2], const float2 (&o)[R / 2]) {
-    const float2 t = mul_twiddle<R, K>(o[K]);
-    x[K] = cadd(e[K], t);
-    x[K + R / 2] = csub(e[K], t);
+  static PDS_HD void run(cplx (&x)[R], const cplx (&e)[R / 2], const cplx (&o)[R / 2]) {
+    butterfly<R, K>(e[K], o[K], x[K], x[K + R / 2]);
     if constexpr (K + 1 < R / 2) Butterflies<R, K + 1>::run(x, e, o);
   }
 };
@@ -147,8 +220,8 @@ struct Butterflies {
 // In-place forward DFT of R points held in registers (natural order in, natural order out).
 template <int R>
 struct Dft {
-  static PDS_HD void run(float2 (&x)[R]) {
-    float2 e[R / 2], o[R / 2];
+  static PDS_HD void run(cplx (&x)[R]) {
+    cplx e[R / 2], o[R / 2];
 #pragma unroll
     for (int i = 0; i < R / 2; ++i) {
       e[i] = x[2 * i];
@@ -162,13 +235,13 @@ struct Dft {
 
 template <>
 struct Dft<1> {
-  static PDS_HD void run(float2 (&)[1]) {}
+  static PDS_HD void run(cplx (&)[1]) {}
 };
 
 template <>
 struct Dft<2> {
-  static PDS_HD void run(float2 (&x)[2]) {
-    const float2 a = x[0], b = x[1];
+  static PDS_HD void run(cplx (&x)[2]) {
+    const cplx a = x[0], b = x[1];
     x[0] = cadd(a, b);
     x[1] = csub(a, b);
   }
@@ -189,13 +262,14 @@ struct FftGeom {
 
 // One unit of the real-FFT split: from Z[k] (= a) and Z[NC-k] (= b), with the window already
 // scaled by 1/2, produce X[k] and X[NC-k] of the N-point real DFT.  w = e^{-2 pi i k / N}.
-PDS_HD void split_pair(float2 a, float2 b, float2 w, float2& xk, float2& xp) {
-  const float er = a.x + b.x, ei = a.y - b.y;  // a + conj(b)
-  const float dr = a.x - b.x, di = a.y + b.y;  // a - conj(b); O = -i * (dr, di) = (di, -dr)
-  const float tr = w.x * di + w.y * dr;        // Re(w * O)
-  const float ti = w.y * di - w.x * dr;        // Im(w * O)
-  xk = make_float2(er + tr, ei + ti);
-  xp = make_float2(er - tr, ti - ei);          // conj(E - T)
+//   E = a + conj(b),  D = a - conj(b),  O = -i D,  T = w O = (-i w) D,
+//   X[k] = E + T,  X[NC-k] = conj(E - T)   (the conjugate is irrelevant for |.|)
+PDS_HD void split_pair(cplx a, cplx b, float2 w, cplx& xk, cplx& xq) {
+  const cplx e = cadd_conj(a, b);
+  const cplx d = csub_conj(a, b);
+  const cplx t = cmul(d, w.y, -w.x);  // -i w = (w.im, -w.re)
+  xk = cadd(e, t);
+  xq = csub(e, t);
 }
 
 }  // namespace pds

@@ -263,30 +263,28 @@ __device__ __forceinline__ void fft_frame(const float* __restrict__ fx, const fl
   constexpr int TS = kTileStride;
   constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
   const int partner = (G - l) % G;
-  const float2* xp = reinterpret_cast<const float2*>(fx) + l;
-  const float2* wp = reinterpret_cast<const float2*>(s_w) + l;
-  float2 z[R1];
-  float energy = 0.f;
+  const cplx* xp = reinterpret_cast<const cplx*>(fx) + l;   // (x[2n], x[2n+1]) is one 64-bit load
+  const cplx* wp = reinterpret_cast<const cplx*>(s_w) + l;
+  cplx z[R1];
+  cplx energy2 = cmake(0.f, 0.f);
+  const cplx last_mask = cmake(last_ok0 ? 1.f : 0.f, last_ok1 ? 1.f : 0.f);
 #pragma unroll
   for (int r = 0; r < R1; ++r) {
     if (r < ROWS) {
-      float2 x = xp[G * r];
-      const float2 w = wp[G * r];
-      z[r] = make_float2(x.x * w.x, x.y * w.y);
+      cplx x = xp[G * r];
+      z[r] = cmul2(x, wp[G * r]);  // window multiply: one FMUL2 per sample pair
       if (MODE == kRowsAny) {
-        x.x = 2 * (G * r + l) < p.L ? x.x : 0.f;
-        x.y = 2 * (G * r + l) + 1 < p.L ? x.y : 0.f;
+        x = cmul2(x, cmake(2 * (G * r + l) < p.L ? 1.f : 0.f, 2 * (G * r + l) + 1 < p.L ? 1.f : 0.f));
       } else if (r == ROWS - 1) {
-        x.x = last_ok0 ? x.x : 0.f;
-        x.y = last_ok1 ? x.y : 0.f;
+        x = cmul2(x, last_mask);
       }
-      energy = fmaf(x.x, x.x, energy);
-      energy = fmaf(x.y, x.y, energy);
+      energy2 = cfma2(x, x, energy2);
     } else {
-      z[r] = make_float2(0.f, 0.f);
+      z[r] = cmake(0.f, 0.f);
     }
   }
   if (want_energy) {
+    float energy = cre(energy2) + cim(energy2);
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) energy += __shfl_xor_sync(0xffffffffu, energy, off, G);
     if (l == 0) *e_slot = energy;
@@ -296,14 +294,15 @@ __device__ __forceinline__ void fft_frame(const float* __restrict__ fx, const fl
 #pragma unroll
   for (int k1 = 1; k1 < R1; ++k1)
     z[k1] = cmul(z[k1], REGTW ? tw_stage[k1] : __ldg(&p.tw_stage[l * R1 + k1]));
+  cplx* cscr = reinterpret_cast<cplx*>(scr);
 #pragma unroll
-  for (int k1 = 0; k1 < R1; ++k1) scr[l * Geo::SCR_STRIDE + k1] = z[k1];
+  for (int k1 = 0; k1 < R1; ++k1) cscr[l * Geo::SCR_STRIDE + k1] = z[k1];
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < NSUB; ++j) {
-    float2 v[G];
+    cplx v[G];
 #pragma unroll
-    for (int n2 = 0; n2 < G; ++n2) v[n2] = scr[n2 * Geo::SCR_STRIDE + l + G * j];
+    for (int n2 = 0; n2 < G; ++n2) v[n2] = cscr[n2 * Geo::SCR_STRIDE + l + G * j];
     Dft<G>::run(v);
 #pragma unroll
     for (int k2 = 0; k2 < G; ++k2) z[j + NSUB * k2] = v[k2];
@@ -313,14 +312,13 @@ __device__ __forceinline__ void fft_frame(const float* __restrict__ fx, const fl
   // real-FFT split: lane l pairs its lower-half registers with the partner's upper half
 #pragma unroll
   for (int m = 0; m < R1 / 2; ++m) {
-    float2 b;
-    b.x = __shfl_sync(0xffffffffu, z[R1 - 1 - m].x, partner, G);
-    b.y = __shfl_sync(0xffffffffu, z[R1 - 1 - m].y, partner, G);
+    cplx b;
+    b.v = __shfl_sync(0xffffffffu, z[R1 - 1 - m].v, partner, G);
     if (l == 0) b = z[(R1 - m) % R1];
     const float2 w = REGTW ? tw_split[m] : __ldg(&p.tw_split[l * (R1 / 2) + m]);
-    float2 xk, xq;
+    cplx xk, xq;
     split_pair(z[m], b, w, xk, xq);
-    float pk = xk.x * xk.x + xk.y * xk.y, pq = xq.x * xq.x + xq.y * xq.y;
+    float pk = cnorm(xk), pq = cnorm(xq);
     if (!POWER) {
       pk = sqrtf(pk);
       pq = sqrtf(pq);
@@ -330,10 +328,10 @@ __device__ __forceinline__ void fft_frame(const float* __restrict__ fx, const fl
     pcol[(NC - k) * TS] = pq;
   }
   if (l == 0) {  // bin NC/2 pairs with itself; its twiddle is -i
-    const float2 a = z[R1 / 2];
-    float2 xk, xq;
+    const cplx a = z[R1 / 2];
+    cplx xk, xq;
     split_pair(a, a, make_float2(0.f, -1.f), xk, xq);
-    float pk = xk.x * xk.x + xk.y * xk.y;
+    float pk = cnorm(xk);
     if (!POWER) pk = sqrtf(pk);
     pcol[(NC / 2) * TS] = pk;
   }
