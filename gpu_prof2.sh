@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-CMD2="python tools/probe_stft.py 600"
-timeout 120 $CMD2 > gpurun_out/plain2.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:stft_fused -s 3 -c 1 -o gpurun_out/prof_x2 -f $CMD2 > gpurun_out/ncu_full.log 2>&1
-echo "full capture rc=$?"; tail -2 gpurun_out/ncu_full.log
+CMD2="python tools/probe_si.py 0"
+timeout 120 $CMD2 > gpurun_out/plain_si.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:si_direct -s 2 -c 1 -o gpurun_out/prof_si -f $CMD2 > gpurun_out/ncu_si.log 2>&1
+echo "full capture rc=$?"; tail -2 gpurun_out/ncu_si.log; cat gpurun_out/plain_si.log

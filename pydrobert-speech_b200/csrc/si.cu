@@ -112,16 +112,44 @@ __global__ void __launch_bounds__(kSiThreads, 2) si_direct_kernel(const __grid_c
 #pragma unroll
           for (int q = 0; q < SPT; ++q) w[q] = w[q + SPT];
         }
-        // pooling: sample r = i0 + q feeds frame t = r / S (window half 0) and t - 1 (half 1)
+        // pooling: sample r = i0 + q feeds frame t = r / S (window half 0) and t - 1 (half 1).
+        // When S is a multiple of SPT a thread's samples share one t: sum them in registers, then a
+        // segmented warp reduction (lanes with equal t are contiguous) leaves one shared-memory
+        // atomic per frame and warp instead of two per sample.
+        if (S % SPT == 0) {
+          const int t = i0 / S, n0 = i0 - t * S;
+          float first_half = 0.f, second_half = 0.f;
 #pragma unroll
-        for (int q = 0; q < SPT; ++q) {
-          const int r = i0 + q;
-          if (r < ny) {
+          for (int q = 0; q < SPT; ++q) {
             float u = REAL ? re[q] * re[q] : re[q] * re[q] + im[q] * im[q];
             if (!POWER) u = sqrtf(u);
-            const int t = r / S, n = r - t * S;
-            if (t < nframes) atomicAdd(&s_acc[t * C + c], s_w[n] * u);
-            if (t >= 1 && t - 1 < nframes) atomicAdd(&s_acc[(t - 1) * C + c], s_w[S + n] * u);
+            if (i0 + q >= ny) u = 0.f;
+            first_half = fmaf(s_w[n0 + q], u, first_half);
+            second_half = fmaf(s_w[S + n0 + q], u, second_half);
+          }
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const int t_other = __shfl_down_sync(0xffffffffu, t, off);
+            const float a = __shfl_down_sync(0xffffffffu, first_half, off);
+            const float b = __shfl_down_sync(0xffffffffu, second_half, off);
+            if (lane + off < 32 && t_other == t) first_half += a, second_half += b;
+          }
+          const int t_prev = __shfl_up_sync(0xffffffffu, t, 1);
+          if (lane == 0 || t_prev != t) {  // segment leader
+            if (t < nframes) atomicAdd(&s_acc[t * C + c], first_half);
+            if (t >= 1 && t - 1 < nframes) atomicAdd(&s_acc[(t - 1) * C + c], second_half);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < SPT; ++q) {
+            const int r = i0 + q;
+            if (r < ny) {
+              float u = REAL ? re[q] * re[q] : re[q] * re[q] + im[q] * im[q];
+              if (!POWER) u = sqrtf(u);
+              const int t = r / S, n = r - t * S;
+              if (t < nframes) atomicAdd(&s_acc[t * C + c], s_w[n] * u);
+              if (t >= 1 && t - 1 < nframes) atomicAdd(&s_acc[(t - 1) * C + c], s_w[S + n] * u);
+            }
           }
         }
       }
