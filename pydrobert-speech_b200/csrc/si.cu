@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fft_core.cuh"
 
 namespace pds {
 
@@ -84,9 +85,11 @@ __global__ void __launch_bounds__(kSiThreads, 2) si_direct_kernel(const __grid_c
       __syncwarp();
       for (int ch = 0; ch < nchunks; ++ch) {
         const int i0 = ch * chunk + lane * SPT;  // first output of this thread (multiple of 8)
-        float re[SPT], im[SPT], w[2 * SPT];
+        // accumulators are packed (re, im) pairs: one FFMA2 per (tap, output) for complex banks
+        cplx acc[SPT];
+        float w[2 * SPT];
 #pragma unroll
-        for (int q = 0; q < SPT; ++q) re[q] = 0.f, im[q] = 0.f;
+        for (int q = 0; q < SPT; ++q) acc[q] = cmake(0.f, 0.f);
         const float4* xs4 = reinterpret_cast<const float4*>(s_x + i0);
         {
           const float4 a = xs4[0], b = xs4[1];
@@ -97,21 +100,24 @@ __global__ void __launch_bounds__(kSiThreads, 2) si_direct_kernel(const __grid_c
             const float4 a = xs4[j0 / 4 + 2], b = xs4[j0 / 4 + 3];
             w[8] = a.x, w[9] = a.y, w[10] = a.z, w[11] = a.w, w[12] = b.x, w[13] = b.y, w[14] = b.z, w[15] = b.w;
           }
-          const float4* g4 = reinterpret_cast<const float4*>(my_h + j0);  // two taps per float4
+          const ulonglong2* g2 = reinterpret_cast<const ulonglong2*>(my_h + j0);  // two taps per load
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
-            const float4 g = g4[jj];
+            const ulonglong2 gg = g2[jj];
+            cplx ga, gb;
+            ga.v = gg.x, gb.v = gg.y;
 #pragma unroll
             for (int q = 0; q < SPT; ++q) {
-              re[q] = fmaf(g.x, w[q + 2 * jj], re[q]);
-              if (!REAL) im[q] = fmaf(g.y, w[q + 2 * jj], im[q]);
-              re[q] = fmaf(g.z, w[q + 2 * jj + 1], re[q]);
-              if (!REAL) im[q] = fmaf(g.w, w[q + 2 * jj + 1], im[q]);
+              acc[q] = cfma2(ga, cmake(w[q + 2 * jj], w[q + 2 * jj]), acc[q]);
+              acc[q] = cfma2(gb, cmake(w[q + 2 * jj + 1], w[q + 2 * jj + 1]), acc[q]);
             }
           }
 #pragma unroll
           for (int q = 0; q < SPT; ++q) w[q] = w[q + SPT];
         }
+        float re[SPT], im[SPT];
+#pragma unroll
+        for (int q = 0; q < SPT; ++q) re[q] = cre(acc[q]), im[q] = cim(acc[q]);
         // pooling: sample r = i0 + q feeds frame t = r / S (window half 0) and t - 1 (half 1).
         // When S is a multiple of SPT a thread's samples share one t: sum them in registers, then a
         // segmented warp reduction (lanes with equal t are contiguous) leaves one shared-memory
