@@ -55,6 +55,14 @@ struct StftParams {
   const int4* pair_desc;    // [npairs] {lo_a * kTileStride, lo_b * kTileStride, groups, weight offset}
   const float* pair_weights;
   int npairs;
+  // tensor-core bank (stft_tc_kernel): work items {n0 | m0 << 16, first 16-bin block, blocks,
+  // fragment offset}, grouped per warp by tc_wstart[0..8]; weights pre-arranged in mma.m16n8k8
+  // B-fragment order, split into tf32 (hi, lo) parts: {b0_hi, b1_hi, b0_lo, b1_lo} per lane and k-step
+  const int4* tc_items;
+  const int* tc_wstart;
+  const float4* tc_frags;
+  int tc_nitems;
+  int tc_p_rows;            // rows of the power-spectrum tile the blocks may touch (multiple of 16)
   int weights_total;        // floats in `pair_weights`
   int weights_in_smem;
   int p_rows;               // rows of the power-spectrum tile: K bins + zero rows read by the padding
@@ -501,6 +509,333 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
 }
 
 // ------------------------------------------------------------------------------------------
+// tensor-core variant of the fused kernel (the default)
+//
+// Same staging and fft phases as stft_fused_kernel; the filter bank is a block-sparse GEMM
+// feat(32 frames x F) = P(32 x K) * W^T(K x F) on the tensor cores (legacy warp-level
+// mma.sync.m16n8k8, tf32 inputs, fp32 accumulate -- the tile is far too small for tcgen05).
+// Precision: P and W are each split into two tf32 terms (hi = top 11 significand bits, lo = the
+// exact remainder) and the three products hi*hi, lo*hi, hi*lo are accumulated: relative error
+// ~2^-20 on sums of non-negative terms, i.e. float32-class (tests pin it against the float64
+// oracle at the same tolerance as the scalar bank).
+//
+// Work split: a run is (8 filters) x (32 frames = two m-tiles) x (a range of 16-bin blocks); the
+// blocks covering the union of the eight bands are cut into at most two runs, and the runs are
+// dealt to the eight warps by the host (longest first), so the phase is balanced even though the
+// high filters are ten times wider than the low ones.  A 16-bin block is two k-steps; k-step s
+// takes bins b0 + 4t + 2s (+1) for t = 0..3, which makes the A-fragment loads from
+// s_P[bin][frame] (row stride 34) bank-conflict free.  Each run stores its partial sums (plain
+// stores) into one of two accumulator tiles laid out like the output block; after the CTA
+// barrier a linear pass adds the two tiles (fixed order: bitwise reproducible), applies floor +
+// log and writes the contiguous (nframes x C) block with coalesced stores.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Shared-memory carve-up of stft_tc_kernel.  Everything but the sample buffer has a compile-time
+// offset (no address arithmetic, no registers); the samples come last.
+template <int N>
+struct TcSmem {
+  using Geo = FftGeom<N>;
+  static constexpr int kProws = ((Geo::NC + 1 + 15) / 16) * 16;  // power-spectrum rows incl. zero padding
+  static constexpr int kMaxItems = 96;
+  static constexpr int oW = 0;                                                    // window [N]
+  static constexpr int oScr = oW + N;                                             // fft exchange scratch
+  static constexpr int oP = oScr + 2 * (kThreads / Geo::G) * Geo::SCR_FLOAT2;     // s_P [kProws][34]
+  static constexpr int oBar = oP + kProws * kTileStride;                          // mbarrier
+  static constexpr int oE = oBar + 4;                                             // frame energies [32]
+  static constexpr int oCtl = oE + kTileFrames;                                   // 2 control blocks x 16 ints
+  static constexpr int oRaw = oCtl + 32;                                          // 2 raw tile descriptors
+  static constexpr int oWstart = oRaw + 16;                                       // item ranges per warp
+  static constexpr int oItems = oWstart + 12;                                     // bank work items (int4)
+  static constexpr int oX = oItems + 4 * kMaxItems;                               // samples [span_max + N]
+  static_assert(oScr % 4 == 0 && oP % 4 == 0 && oBar % 4 == 0 && oItems % 4 == 0 && oX % 4 == 0, "16-byte regions");
+  // after the samples: two accumulator tiles [32 frames][C] (runtime C)
+  static __host__ __device__ constexpr int x_floats(int span_max) { return (span_max + N + 3) & ~3; }
+  static __host__ __device__ constexpr int acc_floats(int C) { return (kTileFrames * C + 3) & ~3; }
+  static __host__ __device__ constexpr size_t bytes(int span_max, int C) {
+    return sizeof(float) * (size_t)(oX + x_floats(span_max) + 2 * acc_floats(C));
+  }
+};
+
+// control block of a tile (ints): what every thread needs, prepared once by thread 0
+enum TcCtl { kCtlFrames = 0, kCtlFlags = 1, kCtlOutLo = 2, kCtlOutHi = 3, kCtlA0 = 4, kCtlA1 = 5, kCtlSpan = 6,
+             kCtlUtt = 7, kCtlStart = 8, kCtlSigLen = 9, kCtlSigOffLo = 10, kCtlSigOffHi = 11 };
+constexpr int kFlagHandStaged = 1;  // some samples (reflected edges, int16, fused pre-processing) are staged by hand
+constexpr int kFlagBulk = 2;        // part of the span arrives by TMA bulk copy
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// thread 0: raw descriptor -> control block
+template <typename T>
+__device__ __noinline__ void tc_prepare(const StftParams& p, const pds_tile& tile, int* __restrict__ c) {
+  const int span = (tile.nframes - 1) * p.S + p.L;
+  int a0, a1;
+  bulk_range<T>(p, tile, span, a0, a1);
+  const long long out_off = tile.out_row * p.C;
+  c[kCtlFrames] = tile.nframes;
+  c[kCtlFlags] = (a1 - a0 < span ? kFlagHandStaged : 0) | (a1 > a0 ? kFlagBulk : 0);
+  c[kCtlOutLo] = (int)(unsigned)(out_off & 0xffffffffll);
+  c[kCtlOutHi] = (int)(out_off >> 32);
+  c[kCtlA0] = a0;
+  c[kCtlA1] = a1;
+  c[kCtlSpan] = span;
+  c[kCtlUtt] = tile.utt;
+  c[kCtlStart] = tile.start;
+  c[kCtlSigLen] = tile.sig_len;
+  c[kCtlSigOffLo] = (int)(unsigned)(tile.sig_off & 0xffffffffll);
+  c[kCtlSigOffHi] = (int)(tile.sig_off >> 32);
+}
+
+__device__ __forceinline__ pds_tile tc_tile_of(const int* __restrict__ c) {
+  pds_tile t;
+  t.sig_off = ((long long)c[kCtlSigOffHi] << 32) | (unsigned)c[kCtlSigOffLo];
+  t.sig_len = c[kCtlSigLen];
+  t.start = c[kCtlStart];
+  t.nframes = c[kCtlFrames];
+  t.utt = c[kCtlUtt];
+  t.out_row = 0;
+  return t;
+}
+
+// thread 0: start the TMA copy of a prepared tile (or complete the phase by hand when it has none)
+template <typename T>
+__device__ __forceinline__ void tc_issue(const StftParams& p, const int* __restrict__ c, float* s_x, uint64_t* s_bar) {
+  if (c[kCtlFlags] & kFlagBulk) {
+    const int a0 = c[kCtlA0], a1 = c[kCtlA1];
+    const long long sig_off = ((long long)c[kCtlSigOffHi] << 32) | (unsigned)c[kCtlSigOffLo];
+    // order the generic-proxy accesses of s_x (made visible by the CTA barrier) before the async write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(s_bar, (a1 - a0) * 4);
+    bulk_copy_g2s(s_x + a0, static_cast<const T*>(p.sig) + sig_off + c[kCtlStart] + a0, (a1 - a0) * 4, s_bar);
+  } else {
+    mbar_arrive(s_bar);
+  }
+}
+
+__device__ __forceinline__ void bank_tc(int warp, int lane, const float* __restrict__ s_P,
+                                        const int4* __restrict__ s_items, const int* __restrict__ s_wstart,
+                                        const StftParams& p, float* __restrict__ s_acc, int acc_stride) {
+  constexpr int TS = kTileStride;
+  const int g = lane >> 2, t = lane & 3;
+  const int C = p.C;
+  const int it_end = s_wstart[warp + 1];
+  const int lane_p = 4 * t * TS + g;                     // this lane's corner of an A fragment
+  const int lane_o = g * C + p.include_energy + 2 * t;   // ... and of a C fragment in an accumulator tile
+  for (int it = s_wstart[warp]; it < it_end; ++it) {
+    const int4 d = s_items[it];
+    const int n0 = d.x & 0xffff, slot = d.x >> 16;
+    const float* __restrict__ pa = s_P + d.y * (16 * TS) + lane_p;
+    const float4* __restrict__ fr = p.tc_frags + d.w + lane;
+    float acc[2][3][4];  // [m-tile][hi*hi | lo*hi | hi*lo][fragment]
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[m][q][i] = 0.f;
+    for (int b = 0; b < d.z; ++b) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const float4 f = __ldg(fr + 32 * s);
+        const uint32_t whi0 = __float_as_uint(f.x), whi1 = __float_as_uint(f.y);
+        const uint32_t wlo0 = __float_as_uint(f.z), wlo1 = __float_as_uint(f.w);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const float* q = pa + 16 * m;
+          const float a[4] = {q[(2 * s) * TS], q[(2 * s) * TS + 8], q[(2 * s + 1) * TS], q[(2 * s + 1) * TS + 8]};
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            hi[i] = __float_as_uint(a[i]) & 0xffffe000u;
+            lo[i] = __float_as_uint(a[i] - __uint_as_float(hi[i]));
+          }
+          mma_tf32(acc[m][0], hi[0], hi[1], hi[2], hi[3], whi0, whi1);
+          mma_tf32(acc[m][1], lo[0], lo[1], lo[2], lo[3], whi0, whi1);
+          mma_tf32(acc[m][2], hi[0], hi[1], hi[2], hi[3], wlo0, wlo1);
+        }
+      }
+      pa += 16 * TS;
+      fr += 64;
+    }
+    float* __restrict__ r0 = s_acc + slot * acc_stride + n0 + lane_o;
+    const bool c0 = n0 + 2 * t < p.F, c1 = n0 + 2 * t + 1 < p.F;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = (acc[m][1][i] + acc[m][2][i]) + acc[m][0][i];  // small terms first
+      float* __restrict__ r = r0 + 16 * m * C;
+      if (c0) r[0] = v[0], r[8 * C] = v[2];
+      if (c1) r[1] = v[1], r[8 * C + 1] = v[3];
+    }
+  }
+}
+
+template <int N, bool POWER, typename T, int MODE>
+__global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
+    stft_tc_kernel(const __grid_constant__ StftParams p) {
+  using Geo = FftGeom<N>;
+  using Lay = TcSmem<N>;
+  constexpr int G = Geo::G, R1 = Geo::R1;
+  constexpr int FPR = kThreads / G;  // frames per round
+  constexpr bool REGTW = (R1 <= 16);
+  constexpr int TS = kTileStride;
+  constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
+
+  extern __shared__ __align__(16) float smem[];
+  float* const s_x = smem + Lay::oX;
+  float* const s_w = smem + Lay::oW;
+  float2* const s_scr = reinterpret_cast<float2*>(smem + Lay::oScr);
+  float* const s_P = smem + Lay::oP;
+  float* const s_e = smem + Lay::oE;
+  uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + Lay::oBar);
+  const int acc_stride = Lay::acc_floats(p.C);
+  float* const s_acc = s_x + Lay::x_floats(p.span_max);
+  int* const s_ctl = reinterpret_cast<int*>(smem + Lay::oCtl);
+  int4* const s_raw = reinterpret_cast<int4*>(smem + Lay::oRaw);
+  int* const s_wstart = reinterpret_cast<int*>(smem + Lay::oWstart);
+  int4* const s_items = reinterpret_cast<int4*>(smem + Lay::oItems);
+
+  const int tid = threadIdx.x;
+  const int sub = tid / G, l = tid % G;
+  const int n_tiles = (int)p.n_tiles, stride = gridDim.x;
+
+  // ---- one-time CTA set-up -------------------------------------------------------------
+  for (int i = tid; i < N; i += kThreads) s_w[i] = p.window[i];
+  for (int i = tid; i < p.tc_nitems; i += kThreads) s_items[i] = p.tc_items[i];
+  if (tid <= kThreads / 32) s_wstart[tid] = p.tc_wstart[tid];
+  for (int i = tid; i < Lay::kProws * TS; i += kThreads) s_P[i] = 0.f;  // incl. the padding rows
+  for (int i = tid; i < p.span_max + N; i += kThreads) s_x[i] = 0.f;    // slack must stay finite
+  for (int i = tid; i < 2 * acc_stride; i += kThreads) s_acc[i] = 0.f;  // single-run filters never touch tile 1
+  int ti = blockIdx.x;
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (ti < n_tiles) {
+      const pds_tile first = p.tiles[ti];
+      tc_prepare<T>(p, first, s_ctl);
+      if (ti + stride < n_tiles) {
+        const int4* src = reinterpret_cast<const int4*>(p.tiles + ti + stride);
+        cp_async16(s_raw + 2, src);
+        cp_async16(s_raw + 3, src + 1);
+      }
+      cp_async_commit();
+    }
+  }
+
+  float2 tw_stage[REGTW ? R1 : 1], tw_split[REGTW ? R1 / 2 : 1];
+  if (REGTW) {
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) tw_stage[k1] = p.tw_stage[l * R1 + k1];
+#pragma unroll
+    for (int m = 0; m < R1 / 2; ++m) tw_split[m] = p.tw_split[l * (R1 / 2) + m];
+  }
+  const bool last_ok0 = 2 * (G * (ROWS - 1) + l) < p.L;
+  const bool last_ok1 = 2 * (G * (ROWS - 1) + l) + 1 < p.L;
+  float2* const scr = s_scr + sub * Geo::SCR_FLOAT2;
+  const bool want_energy = p.include_energy != 0;
+  __syncthreads();
+  if (ti >= n_tiles) return;
+
+  // ---- stage the first tile --------------------------------------------------------------
+  if (tid == 0) tc_issue<T>(p, s_ctl, s_x, s_bar);
+  if (s_ctl[kCtlFlags] & kFlagHandStaged) {
+    stage_samples_slow<T, kThreads>(s_x, p, tc_tile_of(s_ctl), s_ctl[kCtlSpan], s_ctl[kCtlA0], s_ctl[kCtlA1]);
+    __syncthreads();
+  }
+
+  for (int it = 0; ti < n_tiles; ti += stride, ++it) {
+    const int* __restrict__ c = s_ctl + (it & 1) * 16;
+    const int* __restrict__ cn = s_ctl + ((it + 1) & 1) * 16;
+    const int4 c0 = *reinterpret_cast<const int4*>(c);
+    const int nframes = c0.x;
+    float* __restrict__ out_tile = p.out + (((long long)c0.w << 32) | (unsigned)c0.z);
+    const bool has_next = ti + stride < n_tiles;
+    if (tid == 0 && has_next) {
+      // the next tile's descriptor was fetched (cp.async) an iteration ago; fetch the one after it
+      cp_async_wait_all();
+      const int4* raw = s_raw + 2 * ((it + 1) & 1);
+      const int4 r0 = raw[0], r1 = raw[1];
+      pds_tile nt;
+      nt.sig_off = ((long long)r0.y << 32) | (unsigned)r0.x;
+      nt.sig_len = r0.z;
+      nt.start = r0.w;
+      nt.nframes = r1.x;
+      nt.utt = r1.y;
+      nt.out_row = ((long long)r1.w << 32) | (unsigned)r1.z;
+      tc_prepare<T>(p, nt, s_ctl + ((it + 1) & 1) * 16);
+      if (ti + 2 * stride < n_tiles) {
+        const int4* src = reinterpret_cast<const int4*>(p.tiles + ti + 2 * stride);
+        cp_async16(s_raw + 2 * (it & 1), src);
+        cp_async16(s_raw + 2 * (it & 1) + 1, src + 1);
+      }
+      cp_async_commit();
+    }
+    mbar_wait(s_bar, it & 1);
+
+    // ---- fft phase ---------------------------------------------------------------------
+    for (int t0 = 0; t0 < nframes; t0 += FPR) {
+      // sub-groups past the end recompute the last frame (identical writes): full-warp shuffles
+      const int t = min(t0 + sub, nframes - 1);
+      fft_frame<N, POWER, MODE>(s_x + t * p.S, s_w, scr, s_P + t, s_e + t, tw_stage, tw_split, l, last_ok0,
+                                last_ok1, want_energy, p);
+    }
+    __syncthreads();  // s_x is free again, s_P is complete, the next control block is visible
+
+    // ---- start the next tile's TMA copy: it overlaps the bank phase -----------------------
+    if (has_next && tid == 0) tc_issue<T>(p, cn, s_x, s_bar);
+
+    // ---- filter bank on the tensor cores -> accumulator tiles -----------------------------
+    if (want_energy && tid < kTileFrames) {  // energy column (compute.py:392-398), linear domain
+      float v = s_e[tid] * p.inv_L;
+      if (!POWER) v = sqrtf(v);
+      s_acc[tid * p.C] = v;
+    }
+    bank_tc(tid >> 5, tid & 31, s_P, s_items, s_wstart, p, s_acc, acc_stride);
+    if (has_next && (cn[kCtlFlags] & kFlagHandStaged))
+      stage_samples_slow<T, kThreads>(s_x, p, tc_tile_of(cn), cn[kCtlSpan], cn[kCtlA0], cn[kCtlA1]);
+    __syncthreads();  // s_P may be overwritten, hand-staged samples and accumulator tiles are visible
+
+    // ---- add the two accumulator tiles, floor + log, coalesced store ----------------------
+    {
+      const int total = nframes * p.C;
+      const bool use_log = p.use_log != 0;
+      const float log_floor = p.log_floor;
+      constexpr int UNR = 6;  // 32 x 41 coefficients = 5.2 per thread
+      for (int i0 = tid; i0 < total; i0 += UNR * kThreads) {
+        float v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int i = i0 + u * kThreads;
+          v[u] = i < total ? s_acc[i] + s_acc[acc_stride + i] : 1.f;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+          if (use_log) v[u] = fast_log(fmaxf(v[u], log_floor));
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int i = i0 + u * kThreads;
+          if (i < total) out_tile[i] = v[u];
+        }
+      }
+    }
+    // no barrier: the accumulator tiles are next written after the barrier that follows the fft phase
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // software-pipelined variant (one CTA per SM, no CTA-wide barriers in steady state)
 //
 //   warps 0..15  compute : every iteration  A) fft of this warp's two frames of tile i
@@ -544,10 +879,6 @@ __host__ __device__ inline WsLayout ws_layout(int N, int G, int R1, int span_max
   s.wt = take_floats(o, weights_floats);
   s.total = o * 4;
   return s;
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 template <int N, bool POWER, int MODE>
@@ -863,6 +1194,9 @@ struct pds_stft_plan {
   bool fast = false;
   bool ws = false;  // warp-specialised kernel available (N = 512 geometry, plain float32 input)
   size_t ws_smem_bytes = 0;
+  bool tc = false;  // tensor-core bank kernel available (the default fast path)
+  size_t tc_smem_bytes = 0;
+  int tc_grid_limit = 0;
   bool power = false;
   int row_mode = 2;
   int tile_frames = 0;
@@ -900,6 +1234,44 @@ KernelFn pick_fused(bool power, int dtype, int mode) {
   }
 }
 
+template <int N, int MODE>
+KernelFn pick_tc_mode(bool power, int dtype) {
+  if (power) return dtype == PDS_I16 ? stft_tc_kernel<N, true, short, MODE> : stft_tc_kernel<N, true, float, MODE>;
+  return dtype == PDS_I16 ? stft_tc_kernel<N, false, short, MODE> : stft_tc_kernel<N, false, float, MODE>;
+}
+
+template <int N>
+KernelFn pick_tc_n(bool power, int dtype, int mode) {
+  switch (mode) {
+    case kRows13: return pick_tc_mode<N, kRows13>(power, dtype);
+    case kRows16: return pick_tc_mode<N, kRows16>(power, dtype);
+    default: return pick_tc_mode<N, kRowsAny>(power, dtype);
+  }
+}
+
+KernelFn pick_tc(const pds_stft_plan* plan, int dtype) {
+  switch (plan->N) {
+#ifndef PDS_DEV_N512_ONLY
+    case 256: return pick_tc_n<256>(plan->power, dtype, plan->row_mode);
+#endif
+    case 512: return pick_tc_n<512>(plan->power, dtype, plan->row_mode);
+#ifndef PDS_DEV_N512_ONLY
+    case 1024: return pick_tc_n<1024>(plan->power, dtype, plan->row_mode);
+    case 2048: return pick_tc_n<2048>(plan->power, dtype, plan->row_mode);
+#endif
+    default: return nullptr;
+  }
+}
+
+// round-to-nearest split of a weight into two tf32-representable terms
+void split_tf32(float w, float* hi, float* lo) {
+  uint32_t bits;
+  std::memcpy(&bits, &w, 4);
+  bits = (bits + 0x1000u) & 0xffffe000u;
+  std::memcpy(hi, &bits, 4);
+  *lo = w - *hi;
+}
+
 template <int N>
 KernelFn pick_ws(bool power, int mode) {
   switch (mode) {
@@ -912,10 +1284,12 @@ KernelFn pick_ws(bool power, int mode) {
 KernelFn pick_kernel(const pds_stft_plan* plan, int dtype) {
   if (plan->fast) {
     switch (plan->N) {
+#ifndef PDS_DEV_N512_ONLY
       case 256: return pick_fused<256>(plan->power, dtype, plan->row_mode);
-      case 512: return pick_fused<512>(plan->power, dtype, plan->row_mode);
       case 1024: return pick_fused<1024>(plan->power, dtype, plan->row_mode);
       case 2048: return pick_fused<2048>(plan->power, dtype, plan->row_mode);
+#endif
+      case 512: return pick_fused<512>(plan->power, dtype, plan->row_mode);
       default: return nullptr;
     }
   }
@@ -1010,6 +1384,79 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   if (pair_wt.empty()) pair_wt.resize(4, 0.f);
   const int pair_total = (int)pair_wt.size();
 
+  // tensor-core bank: runs (8 filters x 32 frames x range of 16-bin blocks), B fragments
+  const int n_ntiles = (F + 7) / 8;
+  const int n_warps = kThreads / 32;
+  std::vector<int> tc_items;   // 4 ints per run: n0 | slot << 16, first block, blocks, fragment offset
+  std::vector<int> tc_wstart(n_warps + 1, 0);
+  std::vector<float> tc_frags; // 4 floats per (block, k-step, lane)
+  int tc_p_rows = ((K + 15) / 16) * 16;
+  {
+    struct Run { int n0, slot, blk0, nblk, frag; };
+    std::vector<Run> runs;
+    for (int j = 0; j < n_ntiles; ++j) {
+      int lo_bin = K, hi_bin = 0;
+      for (int f = 8 * j; f < std::min(F, 8 * j + 8); ++f)
+        if (d->band_len[f] > 0) {
+          lo_bin = std::min(lo_bin, d->band_lo[f]);
+          hi_bin = std::max(hi_bin, d->band_lo[f] + d->band_len[f]);
+        }
+      const int blk0 = hi_bin > lo_bin ? lo_bin / 16 : 0;
+      const int nblk = hi_bin > lo_bin ? (hi_bin + 15) / 16 - blk0 : 0;
+      const int frag = (int)(tc_frags.size() / 4);
+      for (int b = blk0; b < blk0 + nblk; ++b)
+        for (int s2 = 0; s2 < 2; ++s2)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, t = lane & 3;
+            const int f = 8 * j + g;
+            float w[2] = {0.f, 0.f};
+            for (int c = 0; c < 2; ++c) {
+              const int bin = 16 * b + 4 * t + 2 * s2 + c;
+              if (f < F && bin >= d->band_lo[f] && bin < d->band_lo[f] + d->band_len[f])
+                w[c] = d->weights[d->band_off[f] + (bin - d->band_lo[f])];
+            }
+            float h0, l0, h1, l1;
+            split_tf32(w[0], &h0, &l0);
+            split_tf32(w[1], &h1, &l1);
+            tc_frags.push_back(h0);
+            tc_frags.push_back(h1);
+            tc_frags.push_back(l0);
+            tc_frags.push_back(l1);
+          }
+      // at most two runs per filter group: their partial sums land in accumulator tiles 0 and 1
+      const int first = (nblk + 1) / 2;
+      runs.push_back({8 * j, 0, blk0, first, frag});
+      if (nblk - first > 0) runs.push_back({8 * j, 1, blk0 + first, nblk - first, frag + first * 64});
+      tc_p_rows = std::max(tc_p_rows, 16 * (blk0 + nblk));
+    }
+    // longest-processing-time-first deal to the warps
+    std::vector<int> order(runs.size());
+    for (size_t i = 0; i < runs.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return runs[a].nblk > runs[b].nblk; });
+    std::vector<std::vector<int>> per_warp(n_warps);
+    std::vector<int> load(n_warps, 0);
+    for (int i : order) {
+      int w = 0;
+      for (int q = 1; q < n_warps; ++q)
+        if (load[q] < load[w]) w = q;
+      per_warp[w].push_back(i);
+      load[w] += runs[i].nblk + 1;  // +1: per-run prologue / epilogue
+    }
+    for (int w = 0; w < n_warps; ++w) {
+      tc_wstart[w] = (int)(tc_items.size() / 4);
+      for (int i : per_warp[w]) {
+        const Run& r = runs[i];
+        tc_items.push_back(r.n0 | (r.slot << 16));
+        tc_items.push_back(r.blk0);
+        tc_items.push_back(r.nblk);
+        tc_items.push_back(r.frag);  // float4 index
+      }
+    }
+    tc_wstart[n_warps] = (int)(tc_items.size() / 4);
+    if (tc_frags.empty()) tc_frags.resize(4, 0.f);
+  }
+  const int tc_nitems = (int)(tc_items.size() / 4);
+
   // ---- pick the kernel: shared-memory FFT when the geometry allows, else direct DFT ------
   StftParams& p = plan->params;
   const bool pow2 = (N & (N - 1)) == 0;
@@ -1028,6 +1475,18 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     p.weights_in_smem = (size_t)with.total <= std::min<size_t>(smem_cap, 110 * 1024) ? 1 : 0;
     plan->smem_bytes = p.weights_in_smem ? with.total : without.total;
     if (plan->smem_bytes > smem_cap) plan->fast = false;  // huge frame shift: use the direct kernel
+    if (plan->fast) {
+      size_t tc_bytes = 0;
+      int tc_rows_max = 0, tc_items_max = 0;
+      switch (N) {
+        case 256: tc_bytes = TcSmem<256>::bytes(p.span_max, plan->C), tc_rows_max = TcSmem<256>::kProws, tc_items_max = TcSmem<256>::kMaxItems; break;
+        case 512: tc_bytes = TcSmem<512>::bytes(p.span_max, plan->C), tc_rows_max = TcSmem<512>::kProws, tc_items_max = TcSmem<512>::kMaxItems; break;
+        case 1024: tc_bytes = TcSmem<1024>::bytes(p.span_max, plan->C), tc_rows_max = TcSmem<1024>::kProws, tc_items_max = TcSmem<1024>::kMaxItems; break;
+        default: tc_bytes = TcSmem<2048>::bytes(p.span_max, plan->C), tc_rows_max = TcSmem<2048>::kProws, tc_items_max = TcSmem<2048>::kMaxItems; break;
+      }
+      plan->tc = tc_bytes <= smem_cap && F < 65536 && tc_p_rows <= tc_rows_max && tc_nitems <= tc_items_max;
+      plan->tc_smem_bytes = tc_bytes;
+    }
     if (plan->fast && N == 512 && d->preemph == 0.f && d->dither == 0.f) {
       const WsLayout ws = ws_layout(N, G, R1, p.span_max, p_rows, npairs, plan->C, pair_total);
       plan->ws = (size_t)ws.total <= smem_cap;
@@ -1085,7 +1544,10 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   size_t o_desc = align16(o_off + sizeof(int) * F);
   size_t o_pwt = align16(o_desc + sizeof(int) * 4 * npairs);
   size_t o_wt = align16(o_pwt + sizeof(float) * pair_wt.size());
-  size_t blob_bytes = align16(o_wt + sizeof(float) * wt.size());
+  size_t o_tci = align16(o_wt + sizeof(float) * wt.size());
+  size_t o_tcw = align16(o_tci + sizeof(int) * tc_items.size());
+  size_t o_tcf = align16(o_tcw + sizeof(int) * tc_wstart.size());
+  size_t blob_bytes = align16(o_tcf + sizeof(float) * tc_frags.size());
   std::vector<unsigned char> blob(blob_bytes, 0);
   std::memcpy(blob.data() + o_win, win.data(), sizeof(float) * N);
   if (!tw_stage.empty()) std::memcpy(blob.data() + o_tws, tw_stage.data(), sizeof(float2) * tw_stage.size());
@@ -1097,6 +1559,9 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   std::memcpy(blob.data() + o_desc, desc.data(), sizeof(int) * 4 * npairs);
   std::memcpy(blob.data() + o_pwt, pair_wt.data(), sizeof(float) * pair_wt.size());
   std::memcpy(blob.data() + o_wt, wt.data(), sizeof(float) * wt.size());
+  if (!tc_items.empty()) std::memcpy(blob.data() + o_tci, tc_items.data(), sizeof(int) * tc_items.size());
+  std::memcpy(blob.data() + o_tcw, tc_wstart.data(), sizeof(int) * tc_wstart.size());
+  std::memcpy(blob.data() + o_tcf, tc_frags.data(), sizeof(float) * tc_frags.size());
   err = cudaMalloc(&plan->d_blob, blob_bytes);
   if (err == cudaSuccess) err = cudaMemcpy(plan->d_blob, blob.data(), blob_bytes, cudaMemcpyHostToDevice);
   if (err != cudaSuccess) {
@@ -1115,6 +1580,11 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   p.pair_desc = reinterpret_cast<const int4*>(base + o_desc);
   p.pair_weights = reinterpret_cast<const float*>(base + o_pwt);
   p.npairs = npairs;
+  p.tc_items = reinterpret_cast<const int4*>(base + o_tci);
+  p.tc_wstart = reinterpret_cast<const int*>(base + o_tcw);
+  p.tc_frags = reinterpret_cast<const float4*>(base + o_tcf);
+  p.tc_nitems = tc_nitems;
+  p.tc_p_rows = tc_p_rows;
   p.p_rows = p_rows;
   p.weights = reinterpret_cast<const float*>(base + o_wt);
   p.weights_total = pair_total;
@@ -1138,6 +1608,16 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       return PDS_ERR_CUDA;
     }
   }
+  if (plan->tc) {
+    for (int dt = 0; dt < 2 && plan->tc; ++dt) {
+      err = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_tc(plan, dt)),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->tc_smem_bytes);
+      if (err != cudaSuccess) {
+        cudaGetLastError();
+        plan->tc = false;
+      }
+    }
+  }
   if (plan->ws) {
     err = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_ws<512>(plan->power, plan->row_mode)),
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->ws_smem_bytes);
@@ -1151,6 +1631,12 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(pick_kernel(plan, PDS_F32)),
                                                 plan->fast ? kThreads : kDirectThreads, plan->smem_bytes);
   plan->grid_limit = prop.multiProcessorCount * std::max(1, occ);
+  if (plan->tc) {
+    int occ_tc = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tc, reinterpret_cast<const void*>(pick_tc(plan, PDS_F32)),
+                                                  kThreads, plan->tc_smem_bytes);
+    plan->tc_grid_limit = prop.multiProcessorCount * std::max(1, occ_tc);
+  }
   *out = plan;
   return PDS_OK;
 }
@@ -1256,6 +1742,14 @@ extern "C" int pds_stft_run(pds_stft_plan* plan, const void* d_signal, int sig_d
     const int grid = (int)std::min<int64_t>(n_tiles, plan->num_sms);
     pick_ws<512>(plan->power, plan->row_mode)<<<grid, kWsThreads, plan->ws_smem_bytes,
                                                 static_cast<cudaStream_t>(stream)>>>(p);
+    PDS_CUDA_CHECK(cudaGetLastError());
+    return PDS_OK;
+  }
+  // PDS_STFT_KERNEL=scalar falls back to the CUDA-core bank kernel (A/B runs, tests)
+  const bool want_scalar = force && force[0] == 's';
+  if (plan->tc && !want_scalar) {
+    const int grid = (int)std::min<int64_t>(n_tiles, plan->tc_grid_limit);
+    pick_tc(plan, sig_dtype)<<<grid, kThreads, plan->tc_smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
     PDS_CUDA_CHECK(cudaGetLastError());
     return PDS_OK;
   }
