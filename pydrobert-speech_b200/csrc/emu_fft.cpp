@@ -36,7 +36,13 @@ static void emulate(const float* frame, int L, const float* window, float* P, in
         z[r] = cmake(0.f, 0.f);
       }
     }
-    Dft<R1>::run(z);
+    // like the kernels' kRows13 mode: the last 3/16 of the rows are known zeros
+    constexpr int ROWS13 = (R1 * 13) / 16;
+    constexpr unsigned Z13 = zmask_full<R1>() & ~((1u << ROWS13) - 1u);
+    if (rows_full + row_partial == ROWS13)
+      Dft<R1, Z13>::run(z);
+    else
+      Dft<R1>::run(z);
     for (int k1 = 1; k1 < R1; ++k1) {
       const double a = -two_pi * (double)((long long)l * k1 % NC) / NC;
       z[k1] = cmul(z[k1], make_float2((float)std::cos(a), (float)std::sin(a)));

@@ -217,33 +217,58 @@ struct Butterflies {
   }
 };
 
-// In-place forward DFT of R points held in registers (natural order in, natural order out).
+// Compile-time bookkeeping for inputs known to be exact zeros (the zero padding of a frame that
+// is shorter than the DFT): bit i of ZM set = input i is zero.
 template <int R>
+constexpr unsigned zmask_half(unsigned zm, int odd) {
+  unsigned out = 0;
+  for (int i = 0; i < R / 2; ++i)
+    if (zm & (1u << (2 * i + odd))) out |= 1u << i;
+  return out;
+}
+template <int R>
+constexpr unsigned zmask_full() {
+  return R >= 32 ? 0xffffffffu : ((1u << R) - 1u);
+}
+
+// In-place forward DFT of R points held in registers (natural order in, natural order out).
+// Butterflies whose odd half is all zeros degenerate to copies (no instructions).
+template <int R, unsigned ZM = 0u>
 struct Dft {
   static PDS_HD void run(cplx (&x)[R]) {
+    constexpr unsigned ZE = zmask_half<R>(ZM, 0), ZO = zmask_half<R>(ZM, 1);
     cplx e[R / 2], o[R / 2];
 #pragma unroll
     for (int i = 0; i < R / 2; ++i) {
       e[i] = x[2 * i];
       o[i] = x[2 * i + 1];
     }
-    Dft<R / 2>::run(e);
-    Dft<R / 2>::run(o);
-    Butterflies<R, 0>::run(x, e, o);
+    Dft<R / 2, ZE>::run(e);
+    if constexpr (ZO == zmask_full<R / 2>()) {
+#pragma unroll
+      for (int i = 0; i < R / 2; ++i) x[i] = x[i + R / 2] = e[i];
+    } else {
+      Dft<R / 2, ZO>::run(o);
+      Butterflies<R, 0>::run(x, e, o);
+    }
   }
 };
 
-template <>
-struct Dft<1> {
+template <unsigned ZM>
+struct Dft<1, ZM> {
   static PDS_HD void run(cplx (&)[1]) {}
 };
 
-template <>
-struct Dft<2> {
+template <unsigned ZM>
+struct Dft<2, ZM> {
   static PDS_HD void run(cplx (&x)[2]) {
     const cplx a = x[0], b = x[1];
-    x[0] = cadd(a, b);
-    x[1] = csub(a, b);
+    if constexpr ((ZM & 2u) != 0u) {
+      x[1] = a;  // b == 0
+    } else {
+      x[0] = cadd(a, b);
+      x[1] = csub(a, b);
+    }
   }
 };
 

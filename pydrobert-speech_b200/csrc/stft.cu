@@ -152,12 +152,13 @@ __device__ __forceinline__ void bulk_range(const StftParams& p, const pds_tile& 
 // conversion, fused pre-processing
 template <typename T, int THREADS>
 __device__ __forceinline__ void stage_samples_slow(float* __restrict__ s_x, const StftParams& p,
-                                                   const pds_tile& tile, int span, int a0, int a1) {
+                                                   const pds_tile& tile, int span, int a0, int a1,
+                                                   int tid = threadIdx.x) {
   const T* __restrict__ sig = static_cast<const T*>(p.sig);
   const long long first = tile.start;
   const int skip = a1 - a0;       // elements covered by the bulk copy
   const int todo = span - skip;   // element e of the hand-filled part sits at e (e < a0) or e + skip
-  int e = threadIdx.x;
+  int e = tid;
   for (; e + 3 * THREADS < todo; e += 4 * THREADS) {  // four independent loads in flight
     float v[4];
     int at[4];
@@ -298,7 +299,9 @@ __device__ __forceinline__ void fft_frame(const float* __restrict__ fx, const fl
     if (l == 0) *e_slot = energy;
   }
 
-  Dft<R1>::run(z);
+  // rows >= ROWS are the frame's zero padding: their first-level butterflies are copies
+  constexpr unsigned ZROWS = ROWS >= R1 ? 0u : (zmask_full<R1>() & ~((1u << ROWS) - 1u));
+  Dft<R1, ZROWS>::run(z);
 #pragma unroll
   for (int k1 = 1; k1 < R1; ++k1)
     z[k1] = cmul(z[k1], REGTW ? tw_stage[k1] : __ldg(&p.tw_stage[l * R1 + k1]));
@@ -519,15 +522,12 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
 // ~2^-20 on sums of non-negative terms, i.e. float32-class (tests pin it against the float64
 // oracle at the same tolerance as the scalar bank).
 //
-// Work split: a run is (8 filters) x (32 frames = two m-tiles) x (a range of 16-bin blocks); the
-// blocks covering the union of the eight bands are cut into at most two runs, and the runs are
-// dealt to the eight warps by the host (longest first), so the phase is balanced even though the
-// high filters are ten times wider than the low ones.  A 16-bin block is two k-steps; k-step s
-// takes bins b0 + 4t + 2s (+1) for t = 0..3, which makes the A-fragment loads from
-// s_P[bin][frame] (row stride 34) bank-conflict free.  Each run stores its partial sums (plain
-// stores) into one of two accumulator tiles laid out like the output block; after the CTA
-// barrier a linear pass adds the two tiles (fixed order: bitwise reproducible), applies floor +
-// log and writes the contiguous (nframes x C) block with coalesced stores.
+// Work split: an item is (8 filters) x (16 frames) x (the 16-bin blocks covering the union of
+// the eight bands); items are dealt to the eight warps by the host (longest first).  A 16-bin
+// block is two k-steps; k-step s takes bins b0 + 4t + 2s (+1) for t = 0..3, which makes the
+// A-fragment loads from s_P[bin][frame] (row stride 34) bank-conflict free.  Results go straight
+// from the accumulator fragments to global memory (floor, log, masked by nframes / F): no output
+// staging, no store phase.  The energy column is written by the fft phase.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
@@ -547,19 +547,13 @@ struct TcSmem {
   static constexpr int oScr = oW + N;                                             // fft exchange scratch
   static constexpr int oP = oScr + 2 * (kThreads / Geo::G) * Geo::SCR_FLOAT2;     // s_P [kProws][34]
   static constexpr int oBar = oP + kProws * kTileStride;                          // mbarrier
-  static constexpr int oE = oBar + 4;                                             // frame energies [32]
-  static constexpr int oCtl = oE + kTileFrames;                                   // 2 control blocks x 16 ints
+  static constexpr int oCtl = oBar + 4;                                           // 2 control blocks x 16 ints
   static constexpr int oRaw = oCtl + 32;                                          // 2 raw tile descriptors
   static constexpr int oWstart = oRaw + 16;                                       // item ranges per warp
   static constexpr int oItems = oWstart + 12;                                     // bank work items (int4)
   static constexpr int oX = oItems + 4 * kMaxItems;                               // samples [span_max + N]
   static_assert(oScr % 4 == 0 && oP % 4 == 0 && oBar % 4 == 0 && oItems % 4 == 0 && oX % 4 == 0, "16-byte regions");
-  // after the samples: two accumulator tiles [32 frames][C] (runtime C)
-  static __host__ __device__ constexpr int x_floats(int span_max) { return (span_max + N + 3) & ~3; }
-  static __host__ __device__ constexpr int acc_floats(int C) { return (kTileFrames * C + 3) & ~3; }
-  static __host__ __device__ constexpr size_t bytes(int span_max, int C) {
-    return sizeof(float) * (size_t)(oX + x_floats(span_max) + 2 * acc_floats(C));
-  }
+  static __host__ __device__ constexpr size_t bytes(int span_max) { return sizeof(float) * (size_t)(oX + span_max + N); }
 };
 
 // control block of a tile (ints): what every thread needs, prepared once by thread 0
@@ -626,59 +620,69 @@ __device__ __forceinline__ void tc_issue(const StftParams& p, const int* __restr
 
 __device__ __forceinline__ void bank_tc(int warp, int lane, const float* __restrict__ s_P,
                                         const int4* __restrict__ s_items, const int* __restrict__ s_wstart,
-                                        const StftParams& p, float* __restrict__ s_acc, int acc_stride) {
+                                        const float4* __restrict__ frags, const StftParams& p,
+                                        float* __restrict__ out_tile, int nframes) {
   constexpr int TS = kTileStride;
   const int g = lane >> 2, t = lane & 3;
+  const bool use_log = p.use_log != 0;
+  const float log_floor = p.log_floor;
   const int C = p.C;
   const int it_end = s_wstart[warp + 1];
-  const int lane_p = 4 * t * TS + g;                     // this lane's corner of an A fragment
-  const int lane_o = g * C + p.include_energy + 2 * t;   // ... and of a C fragment in an accumulator tile
+  int lane_p = 4 * t * TS + g;                    // this lane's corner of an A fragment
+  int lane_o = g * C + p.include_energy + 2 * t;  // ... and of a C fragment in the output tile
+  // keep both in registers: re-deriving them from the thread index for every item costs more
+  asm volatile("" : "+r"(lane_p), "+r"(lane_o));
   for (int it = s_wstart[warp]; it < it_end; ++it) {
     const int4 d = s_items[it];
-    const int n0 = d.x & 0xffff, slot = d.x >> 16;
-    const float* __restrict__ pa = s_P + d.y * (16 * TS) + lane_p;
-    const float4* __restrict__ fr = p.tc_frags + d.w + lane;
-    float acc[2][3][4];  // [m-tile][hi*hi | lo*hi | hi*lo][fragment]
+    const int n0 = d.x & 0xffff, m0 = d.x >> 16;
+    if (m0 >= nframes) continue;
+    const float* __restrict__ pa = s_P + d.y * (16 * TS) + m0 + lane_p;
+    const float4* __restrict__ fr = frags + d.w + lane;
+    float acc[2][2][4];  // [k-step parity][main | correction][fragment]
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+    for (int s = 0; s < 2; ++s)
 #pragma unroll
-      for (int q = 0; q < 3; ++q)
+      for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[m][q][i] = 0.f;
-    for (int b = 0; b < d.z; ++b) {
+        for (int i = 0; i < 4; ++i) acc[s][q][i] = 0.f;
+    int left = d.z;  // >= 1 (host)
+#pragma unroll 2
+    do {
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const float4 f = __ldg(fr + 32 * s);
+        const float a[4] = {pa[(2 * s) * TS], pa[(2 * s) * TS + 8], pa[(2 * s + 1) * TS], pa[(2 * s + 1) * TS + 8]};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          hi[i] = __float_as_uint(a[i]) & 0xffffe000u;
+          lo[i] = __float_as_uint(a[i] - __uint_as_float(hi[i]));
+        }
         const uint32_t whi0 = __float_as_uint(f.x), whi1 = __float_as_uint(f.y);
         const uint32_t wlo0 = __float_as_uint(f.z), wlo1 = __float_as_uint(f.w);
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          const float* q = pa + 16 * m;
-          const float a[4] = {q[(2 * s) * TS], q[(2 * s) * TS + 8], q[(2 * s + 1) * TS], q[(2 * s + 1) * TS + 8]};
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            hi[i] = __float_as_uint(a[i]) & 0xffffe000u;
-            lo[i] = __float_as_uint(a[i] - __uint_as_float(hi[i]));
-          }
-          mma_tf32(acc[m][0], hi[0], hi[1], hi[2], hi[3], whi0, whi1);
-          mma_tf32(acc[m][1], lo[0], lo[1], lo[2], lo[3], whi0, whi1);
-          mma_tf32(acc[m][2], hi[0], hi[1], hi[2], hi[3], wlo0, wlo1);
-        }
+        mma_tf32(acc[s][0], hi[0], hi[1], hi[2], hi[3], whi0, whi1);
+        mma_tf32(acc[s][1], lo[0], lo[1], lo[2], lo[3], whi0, whi1);
+        mma_tf32(acc[s][1], hi[0], hi[1], hi[2], hi[3], wlo0, wlo1);
       }
       pa += 16 * TS;
       fr += 64;
+    } while (--left > 0);
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = (acc[0][1][i] + acc[1][1][i]) + (acc[0][0][i] + acc[1][0][i]);  // small terms first
+      if (use_log) v[i] = fast_log(fmaxf(v[i], log_floor));
     }
-    float* __restrict__ r0 = s_acc + slot * acc_stride + n0 + lane_o;
+    float* __restrict__ r0 = out_tile + (m0 * C + n0 + lane_o);
+    float* __restrict__ r1 = r0 + 8 * C;
     const bool c0 = n0 + 2 * t < p.F, c1 = n0 + 2 * t + 1 < p.F;
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      float v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = (acc[m][1][i] + acc[m][2][i]) + acc[m][0][i];  // small terms first
-      float* __restrict__ r = r0 + 16 * m * C;
-      if (c0) r[0] = v[0], r[8 * C] = v[2];
-      if (c1) r[1] = v[1], r[8 * C + 1] = v[3];
+    if (m0 + g < nframes) {
+      if (c0) r0[0] = v[0];
+      if (c1) r0[1] = v[1];
+    }
+    if (m0 + g + 8 < nframes) {
+      if (c0) r1[0] = v[2];
+      if (c1) r1[1] = v[3];
     }
   }
 }
@@ -699,10 +703,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
   float* const s_w = smem + Lay::oW;
   float2* const s_scr = reinterpret_cast<float2*>(smem + Lay::oScr);
   float* const s_P = smem + Lay::oP;
-  float* const s_e = smem + Lay::oE;
   uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + Lay::oBar);
-  const int acc_stride = Lay::acc_floats(p.C);
-  float* const s_acc = s_x + Lay::x_floats(p.span_max);
   int* const s_ctl = reinterpret_cast<int*>(smem + Lay::oCtl);
   int4* const s_raw = reinterpret_cast<int4*>(smem + Lay::oRaw);
   int* const s_wstart = reinterpret_cast<int*>(smem + Lay::oWstart);
@@ -718,7 +719,6 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
   if (tid <= kThreads / 32) s_wstart[tid] = p.tc_wstart[tid];
   for (int i = tid; i < Lay::kProws * TS; i += kThreads) s_P[i] = 0.f;  // incl. the padding rows
   for (int i = tid; i < p.span_max + N; i += kThreads) s_x[i] = 0.f;    // slack must stay finite
-  for (int i = tid; i < 2 * acc_stride; i += kThreads) s_acc[i] = 0.f;  // single-run filters never touch tile 1
   int ti = blockIdx.x;
   if (tid == 0) {
     mbar_init(s_bar, 1);
@@ -789,49 +789,26 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
     for (int t0 = 0; t0 < nframes; t0 += FPR) {
       // sub-groups past the end recompute the last frame (identical writes): full-warp shuffles
       const int t = min(t0 + sub, nframes - 1);
-      fft_frame<N, POWER, MODE>(s_x + t * p.S, s_w, scr, s_P + t, s_e + t, tw_stage, tw_split, l, last_ok0,
+      float energy = 0.f;
+      fft_frame<N, POWER, MODE>(s_x + t * p.S, s_w, scr, s_P + t, &energy, tw_stage, tw_split, l, last_ok0,
                                 last_ok1, want_energy, p);
+      if (want_energy && l == 0) {  // energy column (compute.py:392-398); duplicates write equal values
+        float v = energy * p.inv_L;
+        if (!POWER) v = sqrtf(v);
+        if (p.use_log) v = fast_log(fmaxf(v, p.log_floor));
+        out_tile[t * p.C] = v;
+      }
     }
     __syncthreads();  // s_x is free again, s_P is complete, the next control block is visible
 
     // ---- start the next tile's TMA copy: it overlaps the bank phase -----------------------
     if (has_next && tid == 0) tc_issue<T>(p, cn, s_x, s_bar);
 
-    // ---- filter bank on the tensor cores -> accumulator tiles -----------------------------
-    if (want_energy && tid < kTileFrames) {  // energy column (compute.py:392-398), linear domain
-      float v = s_e[tid] * p.inv_L;
-      if (!POWER) v = sqrtf(v);
-      s_acc[tid * p.C] = v;
-    }
-    bank_tc(tid >> 5, tid & 31, s_P, s_items, s_wstart, p, s_acc, acc_stride);
+    // ---- filter bank on the tensor cores, results straight to global memory --------------
+    bank_tc(tid >> 5, tid & 31, s_P, s_items, s_wstart, p.tc_frags, p, out_tile, nframes);
     if (has_next && (cn[kCtlFlags] & kFlagHandStaged))
       stage_samples_slow<T, kThreads>(s_x, p, tc_tile_of(cn), cn[kCtlSpan], cn[kCtlA0], cn[kCtlA1]);
-    __syncthreads();  // s_P may be overwritten, hand-staged samples and accumulator tiles are visible
-
-    // ---- add the two accumulator tiles, floor + log, coalesced store ----------------------
-    {
-      const int total = nframes * p.C;
-      const bool use_log = p.use_log != 0;
-      const float log_floor = p.log_floor;
-      constexpr int UNR = 6;  // 32 x 41 coefficients = 5.2 per thread
-      for (int i0 = tid; i0 < total; i0 += UNR * kThreads) {
-        float v[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int i = i0 + u * kThreads;
-          v[u] = i < total ? s_acc[i] + s_acc[acc_stride + i] : 1.f;
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u)
-          if (use_log) v[u] = fast_log(fmaxf(v[u], log_floor));
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int i = i0 + u * kThreads;
-          if (i < total) out_tile[i] = v[u];
-        }
-      }
-    }
-    // no barrier: the accumulator tiles are next written after the barrier that follows the fft phase
+    __syncthreads();  // s_P may be overwritten, hand-staged samples are visible
   }
 }
 
@@ -1384,10 +1361,10 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   if (pair_wt.empty()) pair_wt.resize(4, 0.f);
   const int pair_total = (int)pair_wt.size();
 
-  // tensor-core bank: runs (8 filters x 32 frames x range of 16-bin blocks), B fragments
+  // tensor-core bank: items (8 filters x 16 frames x the group's 16-bin blocks), B fragments
   const int n_ntiles = (F + 7) / 8;
   const int n_warps = kThreads / 32;
-  std::vector<int> tc_items;   // 4 ints per run: n0 | slot << 16, first block, blocks, fragment offset
+  std::vector<int> tc_items;   // 4 ints per item: n0 | m0 << 16, first block, blocks, fragment offset
   std::vector<int> tc_wstart(n_warps + 1, 0);
   std::vector<float> tc_frags; // 4 floats per (block, k-step, lane)
   int tc_p_rows = ((K + 15) / 16) * 16;
@@ -1402,7 +1379,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
           hi_bin = std::max(hi_bin, d->band_lo[f] + d->band_len[f]);
         }
       const int blk0 = hi_bin > lo_bin ? lo_bin / 16 : 0;
-      const int nblk = hi_bin > lo_bin ? (hi_bin + 15) / 16 - blk0 : 0;
+      const int nblk = hi_bin > lo_bin ? (hi_bin + 15) / 16 - blk0 : 1;  // all-zero group: one block of zeros
       const int frag = (int)(tc_frags.size() / 4);
       for (int b = blk0; b < blk0 + nblk; ++b)
         for (int s2 = 0; s2 < 2; ++s2)
@@ -1423,10 +1400,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
             tc_frags.push_back(l0);
             tc_frags.push_back(l1);
           }
-      // at most two runs per filter group: their partial sums land in accumulator tiles 0 and 1
-      const int first = (nblk + 1) / 2;
-      runs.push_back({8 * j, 0, blk0, first, frag});
-      if (nblk - first > 0) runs.push_back({8 * j, 1, blk0 + first, nblk - first, frag + first * 64});
+      for (int m0 = 0; m0 < kTileFrames; m0 += 16) runs.push_back({8 * j, m0, blk0, nblk, frag});
       tc_p_rows = std::max(tc_p_rows, 16 * (blk0 + nblk));
     }
     // longest-processing-time-first deal to the warps
@@ -1440,7 +1414,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       for (int q = 1; q < n_warps; ++q)
         if (load[q] < load[w]) w = q;
       per_warp[w].push_back(i);
-      load[w] += runs[i].nblk + 1;  // +1: per-run prologue / epilogue
+      load[w] += runs[i].nblk + 2;  // +2: per-item prologue / epilogue
     }
     for (int w = 0; w < n_warps; ++w) {
       tc_wstart[w] = (int)(tc_items.size() / 4);
@@ -1479,13 +1453,14 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       size_t tc_bytes = 0;
       int tc_rows_max = 0, tc_items_max = 0;
       switch (N) {
-        case 256: tc_bytes = TcSmem<256>::bytes(p.span_max, plan->C), tc_rows_max = TcSmem<256>::kProws, tc_items_max = TcSmem<256>::kMaxItems; break;
-        case 512: tc_bytes = TcSmem<512>::bytes(p.span_max, plan->C), tc_rows_max = TcSmem<512>::kProws, tc_items_max = TcSmem<512>::kMaxItems; break;
-        case 1024: tc_bytes = TcSmem<1024>::bytes(p.span_max, plan->C), tc_rows_max = TcSmem<1024>::kProws, tc_items_max = TcSmem<1024>::kMaxItems; break;
-        default: tc_bytes = TcSmem<2048>::bytes(p.span_max, plan->C), tc_rows_max = TcSmem<2048>::kProws, tc_items_max = TcSmem<2048>::kMaxItems; break;
+        case 256: tc_bytes = TcSmem<256>::bytes(p.span_max), tc_rows_max = TcSmem<256>::kProws, tc_items_max = TcSmem<256>::kMaxItems; break;
+        case 512: tc_bytes = TcSmem<512>::bytes(p.span_max), tc_rows_max = TcSmem<512>::kProws, tc_items_max = TcSmem<512>::kMaxItems; break;
+        case 1024: tc_bytes = TcSmem<1024>::bytes(p.span_max), tc_rows_max = TcSmem<1024>::kProws, tc_items_max = TcSmem<1024>::kMaxItems; break;
+        default: tc_bytes = TcSmem<2048>::bytes(p.span_max), tc_rows_max = TcSmem<2048>::kProws, tc_items_max = TcSmem<2048>::kMaxItems; break;
       }
       plan->tc = tc_bytes <= smem_cap && F < 65536 && tc_p_rows <= tc_rows_max && tc_nitems <= tc_items_max;
       plan->tc_smem_bytes = tc_bytes;
+
     }
     if (plan->fast && N == 512 && d->preemph == 0.f && d->dither == 0.f) {
       const WsLayout ws = ws_layout(N, G, R1, p.span_max, p_rows, npairs, plan->C, pair_total);
