@@ -1,10 +1,8 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv,noheader -lms 50 > gpurun_out/clocks.log &
-SMI=$!
-for k in tc scalar tc scalar; do
-  PDS_STFT_KERNEL=$k timeout 100 python tools/probe_stft.py 10000 > gpurun_out/probe_$k.log 2>&1; echo "probe $k rc=$?"; tail -3 gpurun_out/probe_$k.log | head -2
+timeout 600 python -m pytest tests/test_gpu_post_si.py -x -q -m gpu -k "si_" > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
+for k in fft direct; do
+  PDS_SI_KERNEL=$k timeout 300 python tools/probe_si.py 2 > gpurun_out/probe_si_$k.log 2>&1; echo "si $k rc=$?"; tail -3 gpurun_out/probe_si_$k.log
 done
-kill $SMI
-sort gpurun_out/clocks.log | uniq -c | sort -rn | head -8

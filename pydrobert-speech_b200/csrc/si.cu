@@ -11,6 +11,8 @@
 // shared-memory load of the tap and one of the new sample per kSamplesPerThread*2 FMAs.  Pooling
 // is fused: |y|^p never leaves registers; partial window sums go to shared-memory accumulators.
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -34,6 +36,11 @@ struct SiParams {
   int S, C, M, pad_left;
   int use_log;
   float log_floor;
+  // overlap-save path (si_fft_kernel)
+  const float2* hc;        // [C][32][32] conj(DFT_1024(h_c)) / 1024, element k = lane + 32 * reg at [reg][lane]
+  const float2* tw;        // [32][32]    W_1024^(lane * k1) at [k1][lane]
+  int hops_per_fft;        // pooling hops (S samples each) one 1024-point transform yields
+  int ffts_per_tile;       // transforms that cover the (kSiTileFrames + 1) hops of a full tile
 };
 
 // y index i of the full convolution reads padded samples i-k; padded index q maps to x[q - pad_left].
@@ -170,6 +177,156 @@ __global__ void __launch_bounds__(kSiThreads, 2) si_direct_kernel(const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// overlap-save variant (the default whenever one 1024-point transform yields at least one hop)
+//
+// y_c = x * h_c is evaluated block-wise in the frequency domain, like the reference does
+// (compute.py:893-980), on the in-register FFT of fft_core.cuh: a warp transforms 1024 complex
+// points as 32 lanes x 32 registers (element index = lane + 32 * register on the way in AND on
+// the way out, so products and inverse transforms need no reordering).
+//   phase 1: warp j computes Xc_j = conj(FFT(block j of the staged samples)) into shared memory;
+//            block j starts hops_per_fft * S * j samples into the tile and is 1024 samples long,
+//            its circular convolution with M taps is exact for outputs M-1 .. 1023.
+//   phase 2: warp w takes filters w, w+8, ...; per transform it forms Xc_j * Hc_c (Hc = conj(H)/N,
+//            host, double precision) and runs ONE forward FFT: conj(y) = FFT(conj(Y)/N).  |y|^p of
+//            the valid outputs is pooled with the integration window (two half-window sums per
+//            hop, warp reduction) into the frame accumulators the warp owns.
+// Cost per frame ~ 3/8 * C transforms of 1024 points instead of 2 * M * C * S multiply-adds.
+// ------------------------------------------------------------------------------------------
+constexpr int kSiFftN = 1024;
+constexpr int kSiFftWarps = 8;
+constexpr int kSiFftThreads = 32 * kSiFftWarps;
+using SiGeo = FftGeom<2 * kSiFftN>;  // NC = 1024 complex points: G = 32 lanes, R1 = 32 registers
+static_assert(SiGeo::G == 32 && SiGeo::R1 == 32 && SiGeo::NSUB == 1, "one warp per transform");
+
+struct SiFftSmem {
+  int x, X, tw, scr, w, acc, total;  // float offsets; total in bytes
+};
+__host__ __device__ inline SiFftSmem si_fft_layout(int S, int C, int hops_per_fft, int ffts_per_tile) {
+  SiFftSmem l;
+  int o = 0;
+  auto take = [&](int n) { const int at = o; o += (n + 3) & ~3; return at; };
+  l.x = take((ffts_per_tile - 1) * hops_per_fft * S + kSiFftN);
+  l.X = take(2 * kSiFftN * ffts_per_tile);
+  l.tw = take(2 * kSiFftN);
+  l.scr = take(2 * SiGeo::SCR_FLOAT2 * kSiFftWarps);
+  l.w = take(2 * S);
+  l.acc = take(kSiTileFrames * C);
+  l.total = o * 4;
+  return l;
+}
+
+// 1024-point forward FFT of z (element index = lane + 32 * register, in and out)
+__device__ __forceinline__ void si_fft1024(cplx (&z)[32], int lane, const float2* __restrict__ s_tw,
+                                           cplx* __restrict__ scr) {
+  Dft<32>::run(z);
+#pragma unroll
+  for (int k1 = 1; k1 < 32; ++k1) z[k1] = cmul(z[k1], s_tw[k1 * 32 + lane]);
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) scr[lane * SiGeo::SCR_STRIDE + k1] = z[k1];
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) z[n2] = scr[n2 * SiGeo::SCR_STRIDE + lane];
+  __syncwarp();
+  Dft<32>::run(z);
+}
+
+template <bool POWER>
+__global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_constant__ SiParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int S = p.S, M = p.M, C = p.C, HT = p.hops_per_fft;
+  const SiFftSmem lay = si_fft_layout(S, C, HT, p.ffts_per_tile);
+  float* s_x = smem + lay.x;
+  cplx* s_X = reinterpret_cast<cplx*>(smem + lay.X);
+  float2* s_tw = reinterpret_cast<float2*>(smem + lay.tw);
+  float* s_w = smem + lay.w;
+  float* s_acc = smem + lay.acc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  cplx* scr = reinterpret_cast<cplx*>(smem + lay.scr) + warp * SiGeo::SCR_FLOAT2;
+  float* s_u = reinterpret_cast<float*>(scr);  // the exchange scratch doubles as the |y|^p row
+  const int nx = (p.ffts_per_tile - 1) * HT * S + kSiFftN;
+
+  for (int i = tid; i < 2 * S; i += kSiFftThreads) s_w[i] = p.window[i];
+  for (int i = tid; i < kSiFftN; i += kSiFftThreads) s_tw[i] = p.tw[i];
+
+  for (long long tile_idx = blockIdx.x; tile_idx < p.n_tiles; tile_idx += gridDim.x) {
+    const pds_tile tile = p.tiles[tile_idx];
+    const int nframes = tile.nframes;
+    const int nhops = nframes + 1;
+    const int nfft = (nhops + HT - 1) / HT;
+    const long long y0 = tile.start;  // first pooled sample (index into the full convolution)
+    __syncthreads();
+    // xs[j] = padded sample (y0 - (M-1) + j); zero outside the signal
+    for (int j = tid; j < nx; j += kSiFftThreads) {
+      const long long g = y0 - (M - 1) + j - p.pad_left;
+      s_x[j] = (g >= 0 && g < tile.sig_len) ? p.sig[tile.sig_off + g] : 0.f;
+    }
+    for (int i = tid; i < kSiTileFrames * C; i += kSiFftThreads) s_acc[i] = 0.f;
+    __syncthreads();
+
+    // ---- phase 1: spectra of the sample blocks -----------------------------------------
+    if (warp < nfft) {
+      const float* xb = s_x + warp * HT * S;
+      cplx z[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) z[r] = cmake(xb[lane + 32 * r], 0.f);
+      si_fft1024(z, lane, s_tw, scr);
+      cplx* X = s_X + warp * kSiFftN;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) X[r * 32 + lane] = cmake(cre(z[r]), -cim(z[r]));
+    }
+    __syncthreads();
+
+    // ---- phase 2: one inverse transform per (filter, block), pooling fused -------------
+    for (int c = warp; c < C; c += kSiFftWarps) {
+      const float2* __restrict__ hc = p.hc + (size_t)c * kSiFftN + lane;
+      for (int j = 0; j < nfft; ++j) {
+        const cplx* __restrict__ X = s_X + j * kSiFftN + lane;
+        cplx z[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) z[r] = cmul(X[r * 32], __ldg(hc + r * 32));
+        si_fft1024(z, lane, s_tw, scr);
+        // valid outputs n = M-1 .. M-1 + HT*S - 1  ->  s_u[n - (M-1)]
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const int n = lane + 32 * r - (M - 1);
+          float u = cnorm(z[r]);
+          if (!POWER) u = sqrtf(u);
+          if (n >= 0 && n < HT * S) s_u[n] = u;
+        }
+        __syncwarp();
+        for (int hh = 0; hh < HT; ++hh) {
+          const int gh = j * HT + hh;  // hop index inside the tile
+          if (gh >= nhops) break;
+          float a1 = 0.f, a2 = 0.f;
+          for (int i = lane; i < S; i += 32) {
+            const float u = s_u[hh * S + i];
+            a1 = fmaf(s_w[i], u, a1);
+            a2 = fmaf(s_w[S + i], u, a2);
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+          }
+          if (lane == 0) {  // this warp owns column c of the accumulators
+            if (gh < nframes) s_acc[gh * C + c] += a1;
+            if (gh >= 1) s_acc[(gh - 1) * C + c] += a2;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    float* __restrict__ dst = p.out + tile.out_row * C;
+    for (int i = tid; i < nframes * C; i += kSiFftThreads) {
+      float v = s_acc[i];
+      if (p.use_log) v = __logf(fmaxf(v, p.log_floor));
+      dst[i] = v;
+    }
+  }
+}
+
 }  // namespace pds
 
 using namespace pds;
@@ -180,6 +337,9 @@ struct pds_si_plan {
   bool real = false, power = false;
   size_t smem_bytes = 0;
   int grid_limit = 0;
+  bool fft = false;  // overlap-save kernel usable
+  size_t fft_smem_bytes = 0;
+  int fft_grid_limit = 0;
   SiParams params{};
   void* d_blob = nullptr;
 };
@@ -213,8 +373,38 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
   plan->real = d->is_real != 0, plan->power = d->use_power != 0;
   const size_t nh = (size_t)plan->C * plan->M;
   const size_t o_re = 0, o_im = nh * sizeof(float), o_w = 2 * nh * sizeof(float);
-  const size_t bytes = o_w + 2 * (size_t)plan->S * sizeof(float);
+  // overlap-save tables: usable when a 1024-point block yields at least one whole hop
+  const int hops_per_fft = (kSiFftN - (plan->M - 1)) / plan->S;
+  plan->fft = hops_per_fft >= 1 && plan->M <= kSiFftN;
+  const size_t o_hc = (o_w + 2 * (size_t)plan->S * sizeof(float) + 15) & ~(size_t)15;
+  const size_t o_tw = o_hc + (plan->fft ? (size_t)plan->C * kSiFftN * sizeof(float2) : 0);
+  const size_t bytes = o_tw + (plan->fft ? (size_t)kSiFftN * sizeof(float2) : 0);
   std::vector<unsigned char> blob(bytes, 0);
+  if (plan->fft) {
+    const double two_pi = 6.283185307179586476925286766559;
+    std::vector<double> cs(kSiFftN), sn(kSiFftN);
+    for (int i = 0; i < kSiFftN; ++i) cs[i] = std::cos(two_pi * i / kSiFftN), sn[i] = std::sin(two_pi * i / kSiFftN);
+    float2* hc = reinterpret_cast<float2*>(blob.data() + o_hc);
+    for (int c = 0; c < plan->C; ++c)
+      for (int k = 0; k < kSiFftN; ++k) {
+        double re = 0.0, im = 0.0;  // H[k] = sum_m h[m] e^{-2 pi i k m / N}
+        for (int m = 0; m < plan->M; ++m) {
+          const double hr = d->h_real[(size_t)c * plan->M + m];
+          const double hi = plan->real ? 0.0 : d->h_imag[(size_t)c * plan->M + m];
+          const int a = (int)(((long long)k * m) % kSiFftN);
+          re += hr * cs[a] + hi * sn[a];
+          im += hi * cs[a] - hr * sn[a];
+        }
+        // conj(H) / N at [reg = k / 32][lane = k % 32]
+        hc[(size_t)c * kSiFftN + (k / 32) * 32 + (k % 32)] = make_float2((float)(re / kSiFftN), (float)(-im / kSiFftN));
+      }
+    float2* tw = reinterpret_cast<float2*>(blob.data() + o_tw);
+    for (int k1 = 0; k1 < 32; ++k1)
+      for (int l = 0; l < 32; ++l) {
+        const int a = (l * k1) % kSiFftN;
+        tw[k1 * 32 + l] = make_float2((float)cs[a], (float)(-sn[a]));
+      }
+  }
   memcpy(blob.data() + o_re, d->h_real, nh * sizeof(float));
   if (!plan->real) memcpy(blob.data() + o_im, d->h_imag, nh * sizeof(float));
   memcpy(blob.data() + o_w, d->window, 2 * (size_t)plan->S * sizeof(float));
@@ -233,6 +423,10 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
   p.S = plan->S, p.C = plan->C, p.M = plan->M, p.pad_left = plan->pad_left;
   p.use_log = d->use_log ? 1 : 0;
   p.log_floor = d->log_floor;
+  p.hc = reinterpret_cast<const float2*>(base + o_hc);
+  p.tw = reinterpret_cast<const float2*>(base + o_tw);
+  p.hops_per_fft = plan->fft ? std::min(hops_per_fft, kSiTileFrames + 1) : 0;
+  p.ffts_per_tile = plan->fft ? (kSiTileFrames + 1 + p.hops_per_fft - 1) / p.hops_per_fft : 0;
   const int S = plan->S, M = plan->M, C = plan->C;
   const int Mp = (M + 7) & ~7;
   const int ny_max = (kSiTileFrames + 1) * S;
@@ -260,6 +454,23 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(pick_si(plan)),
                                                 kSiThreads, plan->smem_bytes);
   plan->grid_limit = prop.multiProcessorCount * std::max(1, occ);
+  if (plan->fft) {
+    plan->fft_smem_bytes = si_fft_layout(S, C, p.hops_per_fft, p.ffts_per_tile).total;
+    plan->fft = p.ffts_per_tile <= kSiFftWarps && plan->fft_smem_bytes <= prop.sharedMemPerBlockOptin;
+  }
+  if (plan->fft) {
+    const void* fn = plan->power ? reinterpret_cast<const void*>(si_fft_kernel<true>)
+                                 : reinterpret_cast<const void*>(si_fft_kernel<false>);
+    err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->fft_smem_bytes);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      plan->fft = false;
+    } else {
+      int occ_fft = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_fft, fn, kSiFftThreads, plan->fft_smem_bytes);
+      plan->fft_grid_limit = prop.multiProcessorCount * std::max(1, occ_fft);
+    }
+  }
   *out = plan;
   return PDS_OK;
 }
@@ -322,6 +533,17 @@ extern "C" int pds_si_run(pds_si_plan* plan, const float* d_signal, const pds_ti
   PDS_REQUIRE(d_signal && d_tiles && d_out && n_tiles > 0, "null buffer");
   SiParams p = plan->params;
   p.sig = d_signal, p.tiles = d_tiles, p.n_tiles = n_tiles, p.out = d_out;
+  // PDS_SI_KERNEL=direct forces the time-domain kernel (A/B runs, tests)
+  const char* force = getenv("PDS_SI_KERNEL");
+  if (plan->fft && !(force && force[0] == 'd')) {
+    const int grid = (int)std::min<int64_t>(n_tiles, plan->fft_grid_limit);
+    if (plan->power)
+      si_fft_kernel<true><<<grid, kSiFftThreads, plan->fft_smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+    else
+      si_fft_kernel<false><<<grid, kSiFftThreads, plan->fft_smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+    PDS_CUDA_CHECK(cudaGetLastError());
+    return PDS_OK;
+  }
   const int grid = (int)std::min<int64_t>(n_tiles, plan->grid_limit);
   pick_si(plan)<<<grid, kSiThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
   PDS_CUDA_CHECK(cudaGetLastError());
