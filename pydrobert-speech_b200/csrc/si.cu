@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kSiThreads, 2) si_direct_kernel(const __grid_c
 // Cost per frame ~ 3/8 * C transforms of 1024 points instead of 2 * M * C * S multiply-adds.
 // ------------------------------------------------------------------------------------------
 constexpr int kSiFftN = 1024;
-constexpr int kSiFftWarps = 8;
+constexpr int kSiFftWarps = 12;
 constexpr int kSiFftThreads = 32 * kSiFftWarps;
 using SiGeo = FftGeom<2 * kSiFftN>;  // NC = 1024 complex points: G = 32 lanes, R1 = 32 registers
 static_assert(SiGeo::G == 32 && SiGeo::R1 == 32 && SiGeo::NSUB == 1, "one warp per transform");
@@ -278,44 +278,49 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
     __syncthreads();
 
     // ---- phase 2: one inverse transform per (filter, block), pooling fused -------------
-    for (int c = warp; c < C; c += kSiFftWarps) {
+    // tasks (c, j) are dealt round-robin; a frame receives exactly two contributions (first
+    // half-window from hop t, second from hop t + 1), so the shared-memory atomics below are
+    // order independent (a + b == b + a): results stay bitwise reproducible
+    const int r_lo = (M - 1) / 32, r_hi = (M - 1 + HT * S - 1) / 32;
+    for (int task = warp; task < C * nfft; task += kSiFftWarps) {
+      const int c = task / nfft, j = task - c * nfft;
       const float2* __restrict__ hc = p.hc + (size_t)c * kSiFftN + lane;
-      for (int j = 0; j < nfft; ++j) {
-        const cplx* __restrict__ X = s_X + j * kSiFftN + lane;
-        cplx z[32];
+      const cplx* __restrict__ X = s_X + j * kSiFftN + lane;
+      cplx z[32];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) z[r] = cmul(X[r * 32], __ldg(hc + r * 32));
-        si_fft1024(z, lane, s_tw, scr);
-        // valid outputs n = M-1 .. M-1 + HT*S - 1  ->  s_u[n - (M-1)]
+      for (int r = 0; r < 32; ++r) z[r] = cmul(X[r * 32], __ldg(hc + r * 32));
+      si_fft1024(z, lane, s_tw, scr);
+      // valid outputs n = M-1 .. M-1 + HT*S - 1  ->  s_u[n - (M-1)]
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
+      for (int r = 0; r < 32; ++r) {
+        if (r >= r_lo && r <= r_hi) {  // warp-uniform
           const int n = lane + 32 * r - (M - 1);
           float u = cnorm(z[r]);
-          if (!POWER) u = sqrtf(u);
+          if (!POWER) u = u * rsqrtf(fmaxf(u, 1e-37f));  // |y|; branch free, 2 ulp
           if (n >= 0 && n < HT * S) s_u[n] = u;
         }
-        __syncwarp();
-        for (int hh = 0; hh < HT; ++hh) {
-          const int gh = j * HT + hh;  // hop index inside the tile
-          if (gh >= nhops) break;
-          float a1 = 0.f, a2 = 0.f;
-          for (int i = lane; i < S; i += 32) {
-            const float u = s_u[hh * S + i];
-            a1 = fmaf(s_w[i], u, a1);
-            a2 = fmaf(s_w[S + i], u, a2);
-          }
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) {
-            a1 += __shfl_xor_sync(0xffffffffu, a1, off);
-            a2 += __shfl_xor_sync(0xffffffffu, a2, off);
-          }
-          if (lane == 0) {  // this warp owns column c of the accumulators
-            if (gh < nframes) s_acc[gh * C + c] += a1;
-            if (gh >= 1) s_acc[(gh - 1) * C + c] += a2;
-          }
-        }
-        __syncwarp();
       }
+      __syncwarp();
+      for (int hh = 0; hh < HT; ++hh) {
+        const int gh = j * HT + hh;  // hop index inside the tile
+        if (gh >= nhops) break;
+        float a1 = 0.f, a2 = 0.f;
+        for (int i = lane; i < S; i += 32) {
+          const float u = s_u[hh * S + i];
+          a1 = fmaf(s_w[i], u, a1);
+          a2 = fmaf(s_w[S + i], u, a2);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+          a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+        }
+        if (lane == 0) {
+          if (gh < nframes) atomicAdd(&s_acc[gh * C + c], a1);
+          if (gh >= 1) atomicAdd(&s_acc[(gh - 1) * C + c], a2);
+        }
+      }
+      __syncwarp();
     }
     __syncthreads();
     float* __restrict__ dst = p.out + tile.out_row * C;
