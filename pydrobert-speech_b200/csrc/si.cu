@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kSiThreads, 2) si_direct_kernel(const __grid_c
 // Cost per frame ~ 3/8 * C transforms of 1024 points instead of 2 * M * C * S multiply-adds.
 // ------------------------------------------------------------------------------------------
 constexpr int kSiFftN = 1024;
-constexpr int kSiFftWarps = 12;
+constexpr int kSiFftWarps = 16;
 constexpr int kSiFftThreads = 32 * kSiFftWarps;
 using SiGeo = FftGeom<2 * kSiFftN>;  // NC = 1024 complex points: G = 32 lanes, R1 = 32 registers
 static_assert(SiGeo::G == 32 && SiGeo::R1 == 32 && SiGeo::NSUB == 1, "one warp per transform");
