@@ -281,7 +281,6 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
     // tasks (c, j) are dealt round-robin; a frame receives exactly two contributions (first
     // half-window from hop t, second from hop t + 1), so the shared-memory atomics below are
     // order independent (a + b == b + a): results stay bitwise reproducible
-    const int r_lo = (M - 1) / 32, r_hi = (M - 1 + HT * S - 1) / 32;
     for (int task = warp; task < C * nfft; task += kSiFftWarps) {
       const int c = task / nfft, j = task - c * nfft;
       const float2* __restrict__ hc = p.hc + (size_t)c * kSiFftN + lane;
@@ -290,15 +289,13 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
 #pragma unroll
       for (int r = 0; r < 32; ++r) z[r] = cmul(X[r * 32], __ldg(hc + r * 32));
       si_fft1024(z, lane, s_tw, scr);
-      // valid outputs n = M-1 .. M-1 + HT*S - 1  ->  s_u[n - (M-1)]
+      // |y|^p of all 1024 outputs -> s_u (unconditional: no predicates, coalesced); the pooling
+      // below reads only the valid ones, n = M-1 .. M-1 + HT*S - 1
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
-        if (r >= r_lo && r <= r_hi) {  // warp-uniform
-          const int n = lane + 32 * r - (M - 1);
-          float u = cnorm(z[r]);
-          if (!POWER) u = u * rsqrtf(fmaxf(u, 1e-37f));  // |y|; branch free, 2 ulp
-          if (n >= 0 && n < HT * S) s_u[n] = u;
-        }
+        float u = cnorm(z[r]);
+        if (!POWER) u = u * rsqrtf(fmaxf(u, 1e-37f));  // |y|; branch free, 2 ulp
+        s_u[lane + 32 * r] = u;
       }
       __syncwarp();
       for (int hh = 0; hh < HT; ++hh) {
@@ -306,7 +303,7 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
         if (gh >= nhops) break;
         float a1 = 0.f, a2 = 0.f;
         for (int i = lane; i < S; i += 32) {
-          const float u = s_u[hh * S + i];
+          const float u = s_u[M - 1 + hh * S + i];
           a1 = fmaf(s_w[i], u, a1);
           a2 = fmaf(s_w[S + i], u, a2);
         }
