@@ -216,6 +216,39 @@ __host__ __device__ inline SiFftSmem si_fft_layout(int S, int C, int hops_per_ff
   return l;
 }
 
+__device__ __forceinline__ float approx_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// one hop of the pooling: two half-window sums over S samples, Q = S / 32 elements per lane
+template <int Q>
+__device__ __forceinline__ void si_pool_hop(const float* __restrict__ u, const float* __restrict__ s_w, int S,
+                                            int lane, float& a1, float& a2) {
+  a1 = 0.f, a2 = 0.f;
+  if (Q > 0) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int i = lane + 32 * q;
+      const float v = u[i];
+      a1 = fmaf(s_w[i], v, a1);
+      a2 = fmaf(s_w[S + i], v, a2);
+    }
+  } else {
+    for (int i = lane; i < S; i += 32) {
+      const float v = u[i];
+      a1 = fmaf(s_w[i], v, a1);
+      a2 = fmaf(s_w[S + i], v, a2);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+  }
+}
+
 // 1024-point forward FFT of z (element index = lane + 32 * register, in and out)
 __device__ __forceinline__ void si_fft1024(cplx (&z)[32], int lane, const float2* __restrict__ s_tw,
                                            cplx* __restrict__ scr) {
@@ -294,24 +327,19 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
         float u = cnorm(z[r]);
-        if (!POWER) u = u * rsqrtf(fmaxf(u, 1e-37f));  // |y|; branch free, 2 ulp
+        if (!POWER) u = approx_sqrt(u);  // |y|: one MUFU, 2 ulp, branch free
         s_u[lane + 32 * r] = u;
       }
       __syncwarp();
       for (int hh = 0; hh < HT; ++hh) {
         const int gh = j * HT + hh;  // hop index inside the tile
         if (gh >= nhops) break;
-        float a1 = 0.f, a2 = 0.f;
-        for (int i = lane; i < S; i += 32) {
-          const float u = s_u[M - 1 + hh * S + i];
-          a1 = fmaf(s_w[i], u, a1);
-          a2 = fmaf(s_w[S + i], u, a2);
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          a1 += __shfl_xor_sync(0xffffffffu, a1, off);
-          a2 += __shfl_xor_sync(0xffffffffu, a2, off);
-        }
+        float a1, a2;
+        const float* u = s_u + (M - 1) + hh * S;
+        if (S == 160)  // 10 ms at 16 kHz: fully unrolled
+          si_pool_hop<5>(u, s_w, S, lane, a1, a2);
+        else
+          si_pool_hop<0>(u, s_w, S, lane, a1, a2);
         if (lane == 0) {
           if (gh < nframes) atomicAdd(&s_acc[gh * C + c], a1);
           if (gh >= 1) atomicAdd(&s_acc[(gh - 1) * C + c], a2);
