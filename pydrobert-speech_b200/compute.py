@@ -399,6 +399,20 @@ class ShortTimeFourierTransformFrameComputer(LinearFilterBankFrameComputer):
         from ._gpu import TILE_DTYPE, current_device
         from ._lib import check, get_lib
 
+        device = current_device() if device is None else device
+        frame_off, tiles = self.plan_tiles(offsets, lengths, device, utt_base)
+        d_tiles = torch.from_numpy(tiles.view(np.uint8)).to(device, non_blocking=True)
+        return BatchLayout(frame_off, d_tiles, len(tiles), self.num_coeffs, device)
+
+    def plan_tiles(self, offsets: np.ndarray, lengths: np.ndarray, device=None, utt_base: int = 0,
+                   row_base: int = 0):
+        """Host half of ``plan_batch``: ``(frame_off, tiles)`` with the tile table still on the host
+        (structured array of ``pds_tile``); ``row_base`` is added to every tile's output row."""
+        import ctypes
+
+        from ._gpu import TILE_DTYPE, current_device
+        from ._lib import check, get_lib
+
         lib = get_lib()
         device = current_device() if device is None else device
         plan = self._plan(device)
@@ -417,8 +431,9 @@ class ShortTimeFourierTransformFrameComputer(LinearFilterBankFrameComputer):
                                           tiles.ctypes.data))
             if utt_base:
                 tiles["utt"] += utt_base
-        d_tiles = torch.from_numpy(tiles.view(np.uint8)).to(device, non_blocking=True)
-        return BatchLayout(frame_off, d_tiles, int(n_tiles.value), self.num_coeffs, device)
+            if row_base:
+                tiles["out_row"] += row_base
+        return frame_off, tiles
 
     def run_batch(self, layout: "BatchLayout", d_signal, out=None, preemph: float = 0.0,
                   dither: float = 0.0, dither_first: bool = True, seed: int = 0):

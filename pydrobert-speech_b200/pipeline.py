@@ -18,6 +18,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from .compute import (
+    BatchLayout,
     FrameComputer,
     PackedSignals,
     ShortIntegrationFrameComputer,
@@ -175,16 +176,32 @@ class FeaturePipeline:
             out = np.empty((int(frame_off[-1]), width), dtype=np.float32)
         host_in = torch.from_numpy(packed.data)
         host_out = torch.from_numpy(out)
+        if isinstance(self.computer, ShortTimeFourierTransformFrameComputer):
+            self._run_host_stft(packed, host_in, host_out, frame_off, device, utt_base)
+            return out, frame_off
         copy_in, copy_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
         compute = torch.cuda.current_stream(device)
         in_flight = []  # keep device buffers of the last chunks alive
-        for begin, end in self._chunks(packed.lengths):
+        chunks = self._chunks(packed.lengths)
+
+        def start_copy(index):
+            begin, end = chunks[index]
             first = int(packed.offsets[begin]) // 4 * 4
             last = int(packed.offsets[end - 1] + packed.lengths[end - 1]) if end > begin else first
             with torch.cuda.stream(copy_in):
                 d_sig = host_in[first:last].to(device, non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(copy_in)
+            return d_sig, ready, first
+
+        # the sample copy of chunk k+1 is enqueued BEFORE chunk k is planned: planning uploads the
+        # tile table on the compute stream (behind the wait for chunk k's samples) and blocks the
+        # host, which would otherwise leave the copy engine idle between chunks
+        copies = [start_copy(0)] if chunks else []
+        for index, (begin, end) in enumerate(chunks):
+            if index + 1 < len(chunks):
+                copies.append(start_copy(index + 1))
+            d_sig, ready, first = copies.pop(0)
             compute.wait_event(ready)
             feats, _ = self.run_device(d_sig, packed.offsets[begin:end] - first,
                                        packed.lengths[begin:end], utt_base + begin)
@@ -201,6 +218,104 @@ class FeaturePipeline:
         copy_out.synchronize()
         compute.synchronize()
         return out, frame_off
+
+    def _run_host_stft(self, packed, host_in, host_out, frame_off, device, utt_base):
+        """STFT fast path of ``run_host``: nothing on the host blocks between chunks.
+
+        The tile tables of ALL chunks are built first and uploaded with one copy; samples and
+        features move through three pre-allocated device buffers each (kept across calls), so
+        the loop below only enqueues: H2D copy (copy-in stream) -> fused kernel [-> device
+        post-processors] (current stream) -> D2H copy (copy-out stream), ordered by events.
+        """
+        import torch
+
+        computer = self.computer
+        chunks = self._chunks(packed.lengths)
+        if not chunks or frame_off[-1] == 0:
+            return
+        spans = []
+        for begin, end in chunks:
+            first = int(packed.offsets[begin]) // 4 * 4
+            spans.append((first, int(packed.offsets[end - 1] + packed.lengths[end - 1])))
+        max_samples = max(last - first for first, last in spans)
+        max_rows = max(int(frame_off[end] - frame_off[begin]) for begin, end in chunks)
+        nbuf = 3
+        key = (str(device), host_in.dtype, max_samples, max_rows)
+        cache = getattr(self, "_host_buffers", None)
+        if cache is None or cache[0] != key:
+            cache = (key,
+                     [torch.empty(max_samples, dtype=host_in.dtype, device=device) for _ in range(nbuf)],
+                     [torch.empty((max_rows, computer.num_coeffs), dtype=torch.float32, device=device)
+                      for _ in range(nbuf)],
+                     torch.cuda.Stream(device), torch.cuda.Stream(device))
+            self._host_buffers = cache
+        _, d_in, d_feat, copy_in, copy_out = cache
+        compute = torch.cuda.current_stream(device)
+        copy_in.wait_stream(compute)
+        copy_out.wait_stream(compute)
+        in_free = [None] * nbuf
+        out_free = [None] * nbuf
+        ready = {}
+
+        def start_copy(index):
+            slot = index % nbuf
+            first, last = spans[index]
+            with torch.cuda.stream(copy_in):
+                if in_free[slot] is not None:
+                    copy_in.wait_event(in_free[slot])
+                d_in[slot][: last - first].copy_(host_in[first:last], non_blocking=True)
+                ready[index] = torch.cuda.Event()
+                ready[index].record(copy_in)
+
+        # the first sample copies run while the host builds the tile tables
+        for index in range(min(nbuf, len(chunks))):
+            start_copy(index)
+        parts, counts = [], []
+        for (begin, end), (first, _) in zip(chunks, spans):
+            _, tiles = computer.plan_tiles(packed.offsets[begin:end] - first, packed.lengths[begin:end],
+                                           device, utt_base + begin)
+            parts.append(tiles)
+            counts.append(len(tiles))
+        starts = np.concatenate([[0], np.cumsum(counts)])
+        all_tiles = np.concatenate(parts)
+        d_tiles = torch.from_numpy(all_tiles.view(np.uint8)).to(device)
+        tile_bytes = all_tiles.dtype.itemsize
+        for index, (begin, end) in enumerate(chunks):
+            slot = index % nbuf
+            first, last = spans[index]
+            rows = int(frame_off[end] - frame_off[begin])
+            if index not in ready:
+                start_copy(index)
+            d_sig = d_in[slot][: last - first]
+            compute.wait_event(ready.pop(index))
+            if out_free[slot] is not None:
+                compute.wait_event(out_free[slot])
+            layout = BatchLayout(frame_off[begin : end + 1] - frame_off[begin],
+                                 d_tiles[int(starts[index]) * tile_bytes : int(starts[index + 1]) * tile_bytes],
+                                 counts[index], computer.num_coeffs, device)
+            feats = computer.run_batch(layout, d_sig, out=d_feat[slot][:rows], seed=self.seed, **self._fused_pre)
+            in_free[slot] = torch.cuda.Event()
+            in_free[slot].record(compute)
+            if self._device_post and rows:
+                row_off = None
+                for p in self._device_post:
+                    if isinstance(p, Deltas):
+                        if row_off is None:
+                            row_off = torch.from_numpy(layout.frame_off).to(device)
+                        feats = p.apply_device(feats, row_off)
+                    else:
+                        feats = p.apply_device(feats, out=feats)
+            done = torch.cuda.Event()
+            done.record(compute)
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(done)
+                host_out[int(frame_off[begin]) : int(frame_off[end])].copy_(feats, non_blocking=True)
+                feats.record_stream(copy_out)
+                out_free[slot] = torch.cuda.Event()
+                out_free[slot].record(copy_out)
+        copy_out.synchronize()
+        compute.synchronize()
+        copy_in.synchronize()
 
     def __call__(self, signals: Sequence[np.ndarray]) -> List[np.ndarray]:
         return self.run_list(signals)
