@@ -170,7 +170,7 @@ def run_reference_arm(args, rank):
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -188,11 +188,15 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock over the samples taken inside [t_begin, t_end] (wall clock of the timed
+        region); the sampler is started before the warm-up so that it is already running."""
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -200,27 +204,34 @@ class ClockSampler:
             self.proc.kill()
         self.file.flush()
         self.file.seek(0)
-        clocks, reasons, sm_max = [], set(), None
+        rows, sm_max = [], None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for row in self.file.read().splitlines():
             cells = [c.strip() for c in row.split(",")]
             if len(cells) < 9:
                 continue
             try:
-                clocks.append(float(cells[1]))
+                stamp = datetime.datetime.strptime(cells[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clock = float(cells[1])
                 sm_max = float(cells[2])
             except ValueError:
                 continue
-            for name, cell in zip(names, cells[5:9]):
-                if cell.lower().startswith("active"):
-                    reasons.add(name)
+            active = [name for name, cell in zip(names, cells[5:9]) if cell.lower().startswith("active")]
+            rows.append((stamp, clock, active))
         self.file.close()
         os.unlink(self.file.name)
-        if clocks:
-            out["sm_mhz"] = float(np.median(clocks))
+        inside = [r for r in rows if t_begin is None or (t_begin - 0.02 <= r[0] <= t_end + 0.02)]
+        where = "timed region"
+        if not inside and rows:  # region shorter than the sampling period: nearest samples under the same load
+            mid = 0.5 * (t_begin + t_end)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            where = "nearest to the timed region (same load)"
+        if inside:
+            out["sm_mhz"] = float(np.median([r[1] for r in inside]))
             out["sm_max_mhz"] = sm_max
-            out["samples"] = len(clocks)
-        out["reasons"] = sorted(reasons)
+            out["samples"] = len(inside)
+            out["sampled"] = where
+            out["reasons"] = sorted({name for r in inside for name in r[2]})
         return out
 
 
@@ -271,6 +282,9 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     # a fresh box idles at 120 MHz: spin the same step (untimed) until the clocks have ramped, then
     # do the W warm-up steps the contract asks for
     t_spin = time.perf_counter()
@@ -280,9 +294,7 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    wall_begin = time.time()
     stream = torch.cuda.current_stream(device)
     begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_events = []
@@ -295,7 +307,7 @@ def run_ours(args, rank, local_rank, world):
         kernel_events.append((k0, k1))
     end.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall_begin, time.time()) if rank == 0 else None
     elapsed_ms = begin.elapsed_time(end)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
@@ -328,6 +340,24 @@ def run_ours(args, rank, local_rank, world):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # supplementary: the same corpus as 16-bit PCM (what wav files hold): half the bytes over PCIe
+        e2e_pcm = None
+        if not args.no_pcm:
+            host_pcm = torch.empty(total, dtype=torch.int16).pin_memory()
+            host_pcm.copy_(host_sig.clamp(-32768, 32767).round_().to(torch.int16))
+            packed_pcm = PackedSignals(host_pcm.numpy(), offsets, lengths)
+            pipeline.run_host(packed_pcm, out=host_out.numpy(), device=device)  # warm-up
+            barrier()
+            t1 = time.perf_counter()
+            for _ in range(e2e_steps):
+                pipeline.run_host(packed_pcm, out=host_out.numpy(), device=device)
+            torch.cuda.synchronize(device)
+            tp = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            e2e_pcm = {"value": job_hours * e2e_steps / float(tp.item()), "unit": "audio-hours/sec",
+                       "h2d_bytes_per_step": int(lengths.sum()) * 2 + layout.n_tiles * 32,
+                       "note": "same corpus rounded to int16 PCM host buffers (supplementary; `e2e` is the float32 run)"}
         e2e = {
             "value": job_hours * e2e_steps / float(t.item()),
             "unit": "audio-hours/sec",
@@ -335,6 +365,7 @@ def run_ours(args, rank, local_rank, world):
             "d2h_bytes_per_step": int(frames) * computer.num_coeffs * 4,
             "steps": e2e_steps,
             "api": "pydrobert_speech_b200.pipeline.FeaturePipeline.run_host (pinned host in/out)",
+            "int16_pcm_input": e2e_pcm,
         }
 
     if rank == 0:
@@ -424,6 +455,7 @@ def main():
     parser.add_argument("--utts", type=int, default=N_UTTS, help="utterances per GPU")
     parser.add_argument("--chunk-samples", type=int, default=1 << 26)
     parser.add_argument("--e2e-steps", type=int, default=5)
+    parser.add_argument("--no-pcm", action="store_true", help="skip the supplementary int16 end-to-end run")
     parser.add_argument("--prewarm-s", type=float, default=0.75,
                         help="seconds of untimed launches before the warm-up steps (clock ramp on a cold GPU)")
     parser.add_argument("--no-e2e", action="store_true")

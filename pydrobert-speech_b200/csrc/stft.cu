@@ -156,6 +156,40 @@ __device__ __forceinline__ void stage_samples_slow(float* __restrict__ s_x, cons
                                                    int tid = threadIdx.x) {
   const T* __restrict__ sig = static_cast<const T*>(p.sig);
   const long long first = tile.start;
+  if constexpr (sizeof(T) == 2) {
+    // 16-bit PCM without fused pre-processing: the in-range middle of the span is converted four
+    // samples at a time (8-byte loads); only the reflected ends and a few unaligned samples go
+    // through the per-element path
+    if (p.dither == 0.f && p.preemph == 0.f && a1 == a0) {
+      const int r0 = (int)max(0LL, -first);
+      const int r1 = (int)min((long long)span, (long long)tile.sig_len - first);
+      if (r1 - r0 >= 64) {
+        const T* __restrict__ src = sig + tile.sig_off + first;  // src[j] is in range for r0 <= j < r1
+        const int mis = (int)((reinterpret_cast<uintptr_t>(src + r0) >> 1) & 3);
+        const int j0 = r0 + ((4 - mis) & 3);
+        const int nvec = (r1 - j0) >> 2;
+        const int j1 = j0 + 4 * nvec;
+        if ((j0 & 3) == 0) {
+          for (int v = tid; v < nvec; v += THREADS) {
+            const short4 q = *reinterpret_cast<const short4*>(src + j0 + 4 * v);
+            *reinterpret_cast<float4*>(s_x + j0 + 4 * v) = make_float4((float)q.x, (float)q.y, (float)q.z, (float)q.w);
+          }
+        } else {
+          for (int v = tid; v < nvec; v += THREADS) {
+            const short4 q = *reinterpret_cast<const short4*>(src + j0 + 4 * v);
+            float* dst = s_x + j0 + 4 * v;
+            dst[0] = (float)q.x, dst[1] = (float)q.y, dst[2] = (float)q.z, dst[3] = (float)q.w;
+          }
+        }
+        const int rest = j0 + (span - j1);
+        for (int e = tid; e < rest; e += THREADS) {
+          const int at = e < j0 ? e : e - j0 + j1;
+          s_x[at] = load_sample(sig, tile.sig_off + reflect_index(first + at, tile.sig_len));
+        }
+        return;
+      }
+    }
+  }
   const int skip = a1 - a0;       // elements covered by the bulk copy
   const int todo = span - skip;   // element e of the hand-filled part sits at e (e < a0) or e + skip
   int e = tid;
