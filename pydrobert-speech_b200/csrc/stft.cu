@@ -148,6 +148,32 @@ __device__ __forceinline__ void bulk_range(const StftParams& p, const pds_tile& 
   if (b1 - b0 >= 64) a0 = b0, a1 = b1;
 }
 
+// four samples per thread and trip: aligned vector load, optional pre-emphasis, conversion
+template <typename T, int THREADS, bool PRE, bool ALIGNED_DST>
+__device__ __forceinline__ void stage_vec4(float* __restrict__ s_x, const T* __restrict__ src, int j0, int nvec,
+                                           float c, int tid) {
+  for (int v = tid; v < nvec; v += THREADS) {
+    const int j = j0 + 4 * v;
+    float x0, x1, x2, x3;
+    if constexpr (sizeof(T) == 2) {
+      const short4 q = *reinterpret_cast<const short4*>(src + j);
+      x0 = (float)q.x, x1 = (float)q.y, x2 = (float)q.z, x3 = (float)q.w;
+    } else {
+      const float4 q = *reinterpret_cast<const float4*>(src + j);
+      x0 = q.x, x1 = q.y, x2 = q.z, x3 = q.w;
+    }
+    if (PRE) {
+      const float prev = (float)src[j - 1];
+      x3 -= c * x2, x2 -= c * x1, x1 -= c * x0, x0 -= c * prev;
+    }
+    if (ALIGNED_DST) {
+      *reinterpret_cast<float4*>(s_x + j) = make_float4(x0, x1, x2, x3);
+    } else {
+      s_x[j] = x0, s_x[j + 1] = x1, s_x[j + 2] = x2, s_x[j + 3] = x3;
+    }
+  }
+}
+
 // Cooperative per-element staging of [0, a0) and [a1, span): reflection at the edges, dtype
 // conversion, fused pre-processing
 template <typename T, int THREADS>
@@ -156,38 +182,35 @@ __device__ __forceinline__ void stage_samples_slow(float* __restrict__ s_x, cons
                                                    int tid = threadIdx.x) {
   const T* __restrict__ sig = static_cast<const T*>(p.sig);
   const long long first = tile.start;
-  if constexpr (sizeof(T) == 2) {
-    // 16-bit PCM without fused pre-processing: the in-range middle of the span is converted four
-    // samples at a time (8-byte loads); only the reflected ends and a few unaligned samples go
-    // through the per-element path
-    if (p.dither == 0.f && p.preemph == 0.f && a1 == a0) {
-      const int r0 = (int)max(0LL, -first);
-      const int r1 = (int)min((long long)span, (long long)tile.sig_len - first);
-      if (r1 - r0 >= 64) {
-        const T* __restrict__ src = sig + tile.sig_off + first;  // src[j] is in range for r0 <= j < r1
-        const int mis = (int)((reinterpret_cast<uintptr_t>(src + r0) >> 1) & 3);
-        const int j0 = r0 + ((4 - mis) & 3);
-        const int nvec = (r1 - j0) >> 2;
-        const int j1 = j0 + 4 * nvec;
-        if ((j0 & 3) == 0) {
-          for (int v = tid; v < nvec; v += THREADS) {
-            const short4 q = *reinterpret_cast<const short4*>(src + j0 + 4 * v);
-            *reinterpret_cast<float4*>(s_x + j0 + 4 * v) = make_float4((float)q.x, (float)q.y, (float)q.z, (float)q.w);
-          }
-        } else {
-          for (int v = tid; v < nvec; v += THREADS) {
-            const short4 q = *reinterpret_cast<const short4*>(src + j0 + 4 * v);
-            float* dst = s_x + j0 + 4 * v;
-            dst[0] = (float)q.x, dst[1] = (float)q.y, dst[2] = (float)q.z, dst[3] = (float)q.w;
-          }
-        }
-        const int rest = j0 + (span - j1);
-        for (int e = tid; e < rest; e += THREADS) {
-          const int at = e < j0 ? e : e - j0 + j1;
-          s_x[at] = load_sample(sig, tile.sig_off + reflect_index(first + at, tile.sig_len));
-        }
-        return;
+  // Spans that cannot take the TMA path (16-bit PCM, fused pre-emphasis) but need no random
+  // numbers: the in-range middle is converted / filtered four samples at a time with aligned
+  // vector loads; only the reflected ends and a few unaligned samples go through the per-element
+  // path below.  (pre.py:136-149: y[0] = x[0], y[i] = x[i] - c x[i-1], applied before framing.)
+  if (p.dither == 0.f && a1 == a0 && (sizeof(T) == 2 || p.preemph != 0.f)) {
+    const float c = p.preemph;
+    int r0 = (int)max(0LL, -first);
+    if (c != 0.f && first + r0 == 0) ++r0;  // sample 0 has no predecessor: per-element path
+    const int r1 = (int)min((long long)span, (long long)tile.sig_len - first);
+    if (r1 - r0 >= 64) {
+      const T* __restrict__ src = sig + tile.sig_off + first;  // src[j] is in range for r0 <= j < r1
+      const int mis = (int)((reinterpret_cast<uintptr_t>(src + r0) / sizeof(T)) & 3);
+      const int j0 = r0 + ((4 - mis) & 3);
+      const int nvec = (r1 - j0) >> 2;
+      const int j1 = j0 + 4 * nvec;
+      const bool aligned_dst = (j0 & 3) == 0;
+      if (c != 0.f) {
+        if (aligned_dst) stage_vec4<T, THREADS, true, true>(s_x, src, j0, nvec, c, tid);
+        else stage_vec4<T, THREADS, true, false>(s_x, src, j0, nvec, c, tid);
+      } else {
+        if (aligned_dst) stage_vec4<T, THREADS, false, true>(s_x, src, j0, nvec, c, tid);
+        else stage_vec4<T, THREADS, false, false>(s_x, src, j0, nvec, c, tid);
       }
+      const int rest = j0 + (span - j1);
+      for (int e = tid; e < rest; e += THREADS) {
+        const int at = e < j0 ? e : e - j0 + j1;
+        s_x[at] = preprocessed_sample(sig, tile.sig_off, reflect_index(first + at, tile.sig_len), p, tile.utt);
+      }
+      return;
     }
   }
   const int skip = a1 - a0;       // elements covered by the bulk copy

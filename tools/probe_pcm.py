@@ -34,4 +34,21 @@ for name, sig, out in (("float32", d_f32, feats_a), ("int16", d_i16, feats_b)):
         torch.cuda.synchronize()
         best = min(best, t0.elapsed_time(t1))
     print(f"{name}: {best:.3f} ms  frames/s={layout.rows / (best * 1e-3):.3e}")
+for name, kw in (("float32 + preemph 0.97", dict(preemph=0.97)), ("float32 + dither 1.0", dict(dither=1.0)),
+                 ("int16 + preemph 0.97", dict(preemph=0.97))):
+    sig = d_i16 if name.startswith("int16") else d_f32
+    for _ in range(3):
+        computer.run_batch(layout, sig, out=feats_b, **kw)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        computer.run_batch(layout, sig, out=feats_b, **kw)
+        t1.record()
+        torch.cuda.synchronize()
+        best = min(best, t0.elapsed_time(t1))
+    print(f"{name}: {best:.3f} ms  frames/s={layout.rows / (best * 1e-3):.3e}")
+computer.run_batch(layout, d_i16, out=feats_b)
+torch.cuda.synchronize()
 print("max |float32 - int16| =", float((feats_a - feats_b).abs().max()))
