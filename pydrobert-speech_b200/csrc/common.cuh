@@ -38,10 +38,9 @@ int sm_count(int device);
 #ifdef __CUDACC__
 
 // ---- Philox4x32-10 counter-based generator: the dither stream -----------------------------
-// One standard normal per (seed, utterance, sample) triple, independent of how utterances are
-// batched, tiled or sharded over GPUs (SURVEY.md H5: reference only pins mean/std).
-__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t utt, uint64_t sample) {
-  uint32_t c0 = (uint32_t)sample, c1 = (uint32_t)(sample >> 32), c2 = utt, c3 = 0x5eed5eedu;
+// Four standard normals per Philox call: samples 4*group .. 4*group+3 of utterance `utt`.
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t utt, uint64_t group) {
+  uint32_t c0 = (uint32_t)group, c1 = (uint32_t)(group >> 32), c2 = utt, c3 = 0x5eed5eedu;
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
   for (int round = 0; round < 10; ++round) {
@@ -54,11 +53,25 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t utt, uint
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
-  // Box-Muller on two 32-bit uniforms in (0, 1)
+  // two Box-Muller pairs on four 32-bit uniforms in (0, 1)
   const float u1 = ((float)c0 + 0.5f) * 2.3283064365386963e-10f;
   const float u2 = ((float)c1 + 0.5f) * 2.3283064365386963e-10f;
-  const float radius = sqrtf(-2.0f * __logf(fmaxf(u1, 1e-12f)));
-  return radius * __cosf(6.283185307179586f * u2);
+  const float u3 = ((float)c2 + 0.5f) * 2.3283064365386963e-10f;
+  const float u4 = ((float)c3 + 0.5f) * 2.3283064365386963e-10f;
+  const float ra = sqrtf(-2.0f * __logf(fmaxf(u1, 1e-12f)));
+  const float rb = sqrtf(-2.0f * __logf(fmaxf(u3, 1e-12f)));
+  float sa, ca, sb, cb;
+  __sincosf(6.283185307179586f * u2, &sa, &ca);
+  __sincosf(6.283185307179586f * u4, &sb, &cb);
+  return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+}
+
+// One standard normal per (seed, utterance, sample) triple, independent of how utterances are
+// batched, tiled or sharded over GPUs (SURVEY.md H5: reference only pins mean/std).
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t utt, uint64_t sample) {
+  const float4 n = philox_normal4(seed, utt, sample >> 2);
+  const uint32_t which = (uint32_t)sample & 3u;
+  return which == 0 ? n.x : (which == 1 ? n.y : (which == 2 ? n.z : n.w));
 }
 
 template <typename T>
