@@ -819,7 +819,9 @@ class ShortIntegrationFrameComputer(LinearFilterBankFrameComputer):
         device = current_device()
         plan = self._plan(device)
         d_signal = torch.from_numpy(np.ascontiguousarray(buf, dtype=np.float32)).to(device)
-        tile_frames = 8
+        from ._lib import get_lib
+
+        tile_frames = int(get_lib().pds_si_tile_frames(plan.handle))
         starts = np.arange(first_frame, first_frame + nframes, tile_frames)
         tiles = np.zeros(len(starts), dtype=TILE_DTYPE)
         tiles["sig_off"] = 0

@@ -39,8 +39,9 @@ struct SiParams {
   // overlap-save path (si_fft_kernel)
   const float2* hc;        // [C][32][32] conj(DFT_1024(h_c)) / 1024, element k = lane + 32 * reg at [reg][lane]
   const float2* tw;        // [32][32]    W_1024^(lane * k1) at [k1][lane]
-  int hops_per_fft;        // pooling hops (S samples each) one 1024-point transform yields
-  int ffts_per_tile;       // transforms that cover the (kSiTileFrames + 1) hops of a full tile
+  int valid_per_fft;       // exact outputs of one 1024-point block: 1024 - (M - 1)
+  int ffts_per_tile;       // blocks that cover the (tile_frames + 1) * S pooled samples of a full tile
+  int tile_frames;         // frames per tile on this path
 };
 
 // y index i of the full convolution reads padded samples i-k; padded index q maps to x[q - pad_left].
@@ -178,40 +179,45 @@ __global__ void __launch_bounds__(kSiThreads, 2) si_direct_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------
-// overlap-save variant (the default whenever one 1024-point transform yields at least one hop)
+// overlap-save variant (the default whenever three 1024-point blocks cover at least two hops)
 //
 // y_c = x * h_c is evaluated block-wise in the frequency domain, like the reference does
 // (compute.py:893-980), on the in-register FFT of fft_core.cuh: a warp transforms 1024 complex
 // points as 32 lanes x 32 registers (element index = lane + 32 * register on the way in AND on
 // the way out, so products and inverse transforms need no reordering).
-//   phase 1: warp j computes Xc_j = conj(FFT(block j of the staged samples)) into shared memory;
-//            block j starts hops_per_fft * S * j samples into the tile and is 1024 samples long,
-//            its circular convolution with M taps is exact for outputs M-1 .. 1023.
-//   phase 2: warp w takes filters w, w+8, ...; per transform it forms Xc_j * Hc_c (Hc = conj(H)/N,
+//   geometry: a block of 1024 samples yields V = 1024 - (M - 1) exact outputs; a tile is the
+//            largest number of frames whose (frames + 1) * S pooled samples fit in three blocks
+//            (C4: V = 637, 10 frames), so no output is wasted on hop alignment: blocks advance
+//            by V samples and a pooling hop may straddle two of them.
+//   phase 1: warp j computes Xc_j = conj(FFT(block j of the staged samples)) into shared memory.
+//   phase 2: warp w owns filters w, w + 14, ...; per block it forms Xc_j * Hc_c (Hc = conj(H)/N,
 //            host, double precision) and runs ONE forward FFT: conj(y) = FFT(conj(Y)/N).  |y|^p of
-//            the valid outputs is pooled with the integration window (two half-window sums per
-//            hop, warp reduction) into the frame accumulators the warp owns.
-// Cost per frame ~ 3/8 * C transforms of 1024 points instead of 2 * M * C * S multiply-adds.
+//            all outputs goes to the warp's scratch row; for every hop the block touches, two
+//            half-window sums (warp reduction) are added to the frame accumulators of column c.
+//            One warp visits a filter's blocks in order, so the sums are bitwise reproducible.
+// Cost per frame ~ 0.3 * C transforms of 1024 points instead of 2 * M * C * S multiply-adds.
 // ------------------------------------------------------------------------------------------
 constexpr int kSiFftN = 1024;
 constexpr int kSiFftWarps = 16;
 constexpr int kSiFftThreads = 32 * kSiFftWarps;
+constexpr int kSiFftBlocks = 3;   // blocks per full tile
+constexpr int kSiFftMaxTileFrames = 24;
 using SiGeo = FftGeom<2 * kSiFftN>;  // NC = 1024 complex points: G = 32 lanes, R1 = 32 registers
 static_assert(SiGeo::G == 32 && SiGeo::R1 == 32 && SiGeo::NSUB == 1, "one warp per transform");
 
 struct SiFftSmem {
   int x, X, tw, scr, w, acc, total;  // float offsets; total in bytes
 };
-__host__ __device__ inline SiFftSmem si_fft_layout(int S, int C, int hops_per_fft, int ffts_per_tile) {
+__host__ __device__ inline SiFftSmem si_fft_layout(int S, int C, int valid, int nblocks, int tile_frames) {
   SiFftSmem l;
   int o = 0;
   auto take = [&](int n) { const int at = o; o += (n + 3) & ~3; return at; };
-  l.x = take((ffts_per_tile - 1) * hops_per_fft * S + kSiFftN);
-  l.X = take(2 * kSiFftN * ffts_per_tile);
+  l.x = take((nblocks - 1) * valid + kSiFftN);
+  l.X = take(2 * kSiFftN * nblocks);
   l.tw = take(2 * kSiFftN);
   l.scr = take(2 * SiGeo::SCR_FLOAT2 * kSiFftWarps);
   l.w = take(2 * S);
-  l.acc = take(kSiTileFrames * C);
+  l.acc = take(2 * nblocks * (tile_frames + 1) * C);  // [block][hop][half][C] partial window sums
   l.total = o * 4;
   return l;
 }
@@ -220,33 +226,6 @@ __device__ __forceinline__ float approx_sqrt(float x) {
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-
-// one hop of the pooling: two half-window sums over S samples, Q = S / 32 elements per lane
-template <int Q>
-__device__ __forceinline__ void si_pool_hop(const float* __restrict__ u, const float* __restrict__ s_w, int S,
-                                            int lane, float& a1, float& a2) {
-  a1 = 0.f, a2 = 0.f;
-  if (Q > 0) {
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const int i = lane + 32 * q;
-      const float v = u[i];
-      a1 = fmaf(s_w[i], v, a1);
-      a2 = fmaf(s_w[S + i], v, a2);
-    }
-  } else {
-    for (int i = lane; i < S; i += 32) {
-      const float v = u[i];
-      a1 = fmaf(s_w[i], v, a1);
-      a2 = fmaf(s_w[S + i], v, a2);
-    }
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    a1 += __shfl_xor_sync(0xffffffffu, a1, off);
-    a2 += __shfl_xor_sync(0xffffffffu, a2, off);
-  }
 }
 
 // 1024-point forward FFT of z (element index = lane + 32 * register, in and out)
@@ -267,8 +246,8 @@ __device__ __forceinline__ void si_fft1024(cplx (&z)[32], int lane, const float2
 template <bool POWER>
 __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_constant__ SiParams p) {
   extern __shared__ __align__(16) float smem[];
-  const int S = p.S, M = p.M, C = p.C, HT = p.hops_per_fft;
-  const SiFftSmem lay = si_fft_layout(S, C, HT, p.ffts_per_tile);
+  const int S = p.S, M = p.M, C = p.C, V = p.valid_per_fft, TF = p.tile_frames;
+  const SiFftSmem lay = si_fft_layout(S, C, V, p.ffts_per_tile, TF);
   float* s_x = smem + lay.x;
   cplx* s_X = reinterpret_cast<cplx*>(smem + lay.X);
   float2* s_tw = reinterpret_cast<float2*>(smem + lay.tw);
@@ -277,7 +256,7 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   cplx* scr = reinterpret_cast<cplx*>(smem + lay.scr) + warp * SiGeo::SCR_FLOAT2;
   float* s_u = reinterpret_cast<float*>(scr);  // the exchange scratch doubles as the |y|^p row
-  const int nx = (p.ffts_per_tile - 1) * HT * S + kSiFftN;
+  const int nx = (p.ffts_per_tile - 1) * V + kSiFftN;
 
   for (int i = tid; i < 2 * S; i += kSiFftThreads) s_w[i] = p.window[i];
   for (int i = tid; i < kSiFftN; i += kSiFftThreads) s_tw[i] = p.tw[i];
@@ -285,21 +264,21 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
   for (long long tile_idx = blockIdx.x; tile_idx < p.n_tiles; tile_idx += gridDim.x) {
     const pds_tile tile = p.tiles[tile_idx];
     const int nframes = tile.nframes;
-    const int nhops = nframes + 1;
-    const int nfft = (nhops + HT - 1) / HT;
-    const long long y0 = tile.start;  // first pooled sample (index into the full convolution)
+    const int ny = (nframes + 1) * S;      // pooled samples of this tile
+    const int nfft = (ny + V - 1) / V;     // blocks that cover them
+    const long long y0 = tile.start;       // first pooled sample (index into the full convolution)
     __syncthreads();
     // xs[j] = padded sample (y0 - (M-1) + j); zero outside the signal
     for (int j = tid; j < nx; j += kSiFftThreads) {
       const long long g = y0 - (M - 1) + j - p.pad_left;
       s_x[j] = (g >= 0 && g < tile.sig_len) ? p.sig[tile.sig_off + g] : 0.f;
     }
-    for (int i = tid; i < kSiTileFrames * C; i += kSiFftThreads) s_acc[i] = 0.f;
+    for (int i = tid; i < 2 * p.ffts_per_tile * (TF + 1) * C; i += kSiFftThreads) s_acc[i] = 0.f;
     __syncthreads();
 
     // ---- phase 1: spectra of the sample blocks -----------------------------------------
     if (warp < nfft) {
-      const float* xb = s_x + warp * HT * S;
+      const float* xb = s_x + warp * V;
       cplx z[32];
 #pragma unroll
       for (int r = 0; r < 32; ++r) z[r] = cmake(xb[lane + 32 * r], 0.f);
@@ -310,10 +289,10 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
     }
     __syncthreads();
 
-    // ---- phase 2: one inverse transform per (filter, block), pooling fused -------------
-    // tasks (c, j) are dealt round-robin; a frame receives exactly two contributions (first
-    // half-window from hop t, second from hop t + 1), so the shared-memory atomics below are
-    // order independent (a + b == b + a): results stay bitwise reproducible
+    // ---- phase 2: one transform per (filter, block), pooling fused -----------------------
+    // tasks (c, j) are dealt round-robin over the warps; each task writes the half-window sums
+    // of the hops its block touches into slots of its own ([block][hop][half][c]), which the
+    // final pass adds in a fixed order: bitwise reproducible without atomics
     for (int task = warp; task < C * nfft; task += kSiFftWarps) {
       const int c = task / nfft, j = task - c * nfft;
       const float2* __restrict__ hc = p.hc + (size_t)c * kSiFftN + lane;
@@ -322,8 +301,8 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
 #pragma unroll
       for (int r = 0; r < 32; ++r) z[r] = cmul(X[r * 32], __ldg(hc + r * 32));
       si_fft1024(z, lane, s_tw, scr);
-      // |y|^p of all 1024 outputs -> s_u (unconditional: no predicates, coalesced); the pooling
-      // below reads only the valid ones, n = M-1 .. M-1 + HT*S - 1
+      // |y|^p of all 1024 outputs -> s_u (no predicates, coalesced); output n >= M-1 is pooled
+      // sample j*V + n - (M-1) of the tile
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
         float u = cnorm(z[r]);
@@ -331,18 +310,26 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
         s_u[lane + 32 * r] = u;
       }
       __syncwarp();
-      for (int hh = 0; hh < HT; ++hh) {
-        const int gh = j * HT + hh;  // hop index inside the tile
-        if (gh >= nhops) break;
-        float a1, a2;
-        const float* u = s_u + (M - 1) + hh * S;
-        if (S == 160)  // 10 ms at 16 kHz: fully unrolled
-          si_pool_hop<5>(u, s_w, S, lane, a1, a2);
-        else
-          si_pool_hop<0>(u, s_w, S, lane, a1, a2);
+      const int lo_blk = j * V, hi_blk = min(lo_blk + V, ny);
+      const float* __restrict__ ub = s_u + (M - 1) - lo_blk;  // ub[r] = |y|^p of pooled sample r
+      float* __restrict__ part = s_acc + (size_t)j * 2 * (TF + 1) * C + c;
+      for (int h = lo_blk / S; h * S < hi_blk; ++h) {
+        const int lo = max(h * S, lo_blk), hi = min(h * S + S, hi_blk);
+        const float* __restrict__ w1 = s_w - h * S;  // first half-window, indexed by r
+        float a1 = 0.f, a2 = 0.f;
+        for (int r = lo + lane; r < hi; r += 32) {
+          const float u = ub[r];
+          a1 = fmaf(w1[r], u, a1);
+          a2 = fmaf(w1[S + r], u, a2);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+          a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+        }
         if (lane == 0) {
-          if (gh < nframes) atomicAdd(&s_acc[gh * C + c], a1);
-          if (gh >= 1) atomicAdd(&s_acc[(gh - 1) * C + c], a2);
+          part[(2 * h) * C] = a1;
+          part[(2 * h + 1) * C] = a2;
         }
       }
       __syncwarp();
@@ -350,7 +337,12 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
     __syncthreads();
     float* __restrict__ dst = p.out + tile.out_row * C;
     for (int i = tid; i < nframes * C; i += kSiFftThreads) {
-      float v = s_acc[i];
+      const int t = i / C, c = i - t * C;
+      float v = 0.f;
+      for (int j = 0; j < nfft; ++j) {  // frame t = first half-window of hop t + second of hop t + 1
+        const float* __restrict__ part = s_acc + (size_t)j * 2 * (TF + 1) * C + c;
+        v += part[(2 * t) * C] + part[(2 * t + 3) * C];
+      }
       if (p.use_log) v = __logf(fmaxf(v, p.log_floor));
       dst[i] = v;
     }
@@ -367,6 +359,7 @@ struct pds_si_plan {
   bool real = false, power = false;
   size_t smem_bytes = 0;
   int grid_limit = 0;
+  int tile_frames = kSiTileFrames;
   bool fft = false;  // overlap-save kernel usable
   size_t fft_smem_bytes = 0;
   int fft_grid_limit = 0;
@@ -404,8 +397,12 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
   const size_t nh = (size_t)plan->C * plan->M;
   const size_t o_re = 0, o_im = nh * sizeof(float), o_w = 2 * nh * sizeof(float);
   // overlap-save tables: usable when a 1024-point block yields at least one whole hop
-  const int hops_per_fft = (kSiFftN - (plan->M - 1)) / plan->S;
-  plan->fft = hops_per_fft >= 1 && plan->M <= kSiFftN;
+  // (PDS_SI_KERNEL=direct forces the time-domain kernel: A/B runs, tests)
+  const int valid_per_fft = kSiFftN - (plan->M - 1);
+  const int fft_tile_frames =
+      valid_per_fft > 0 ? std::min(kSiFftMaxTileFrames, (kSiFftBlocks * valid_per_fft) / plan->S - 1) : 0;
+  const char* force = getenv("PDS_SI_KERNEL");
+  plan->fft = fft_tile_frames >= 1 && !(force && force[0] == 'd');
   const size_t o_hc = (o_w + 2 * (size_t)plan->S * sizeof(float) + 15) & ~(size_t)15;
   const size_t o_tw = o_hc + (plan->fft ? (size_t)plan->C * kSiFftN * sizeof(float2) : 0);
   const size_t bytes = o_tw + (plan->fft ? (size_t)kSiFftN * sizeof(float2) : 0);
@@ -455,8 +452,9 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
   p.log_floor = d->log_floor;
   p.hc = reinterpret_cast<const float2*>(base + o_hc);
   p.tw = reinterpret_cast<const float2*>(base + o_tw);
-  p.hops_per_fft = plan->fft ? std::min(hops_per_fft, kSiTileFrames + 1) : 0;
-  p.ffts_per_tile = plan->fft ? (kSiTileFrames + 1 + p.hops_per_fft - 1) / p.hops_per_fft : 0;
+  p.valid_per_fft = valid_per_fft;
+  p.tile_frames = plan->fft ? fft_tile_frames : kSiTileFrames;
+  p.ffts_per_tile = plan->fft ? ((fft_tile_frames + 1) * plan->S + valid_per_fft - 1) / valid_per_fft : 0;
   const int S = plan->S, M = plan->M, C = plan->C;
   const int Mp = (M + 7) & ~7;
   const int ny_max = (kSiTileFrames + 1) * S;
@@ -485,7 +483,7 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
                                                 kSiThreads, plan->smem_bytes);
   plan->grid_limit = prop.multiProcessorCount * std::max(1, occ);
   if (plan->fft) {
-    plan->fft_smem_bytes = si_fft_layout(S, C, p.hops_per_fft, p.ffts_per_tile).total;
+    plan->fft_smem_bytes = si_fft_layout(S, C, p.valid_per_fft, p.ffts_per_tile, p.tile_frames).total;
     plan->fft = p.ffts_per_tile <= kSiFftWarps && plan->fft_smem_bytes <= prop.sharedMemPerBlockOptin;
   }
   if (plan->fft) {
@@ -501,6 +499,8 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
       plan->fft_grid_limit = prop.multiProcessorCount * std::max(1, occ_fft);
     }
   }
+  plan->tile_frames = plan->fft ? p.tile_frames : kSiTileFrames;
+  p.tile_frames = plan->tile_frames;
   *out = plan;
   return PDS_OK;
 }
@@ -518,7 +518,7 @@ extern "C" int64_t pds_si_num_frames(const pds_si_plan* plan, int64_t sig_len) {
   return t > 0 ? t : 0;
 }
 
-extern "C" int pds_si_tile_frames(const pds_si_plan*) { return kSiTileFrames; }
+extern "C" int pds_si_tile_frames(const pds_si_plan* plan) { return plan ? plan->tile_frames : kSiTileFrames; }
 
 extern "C" int pds_si_layout(const pds_si_plan* plan, int64_t n_utts, const int64_t* sig_len,
                              int64_t* frame_off, int64_t* n_tiles) {
@@ -530,7 +530,7 @@ extern "C" int pds_si_layout(const pds_si_plan* plan, int64_t n_utts, const int6
     frame_off[u] = rows;
     const int64_t t = pds_si_num_frames(plan, sig_len[u]);
     rows += t;
-    tiles += (t + kSiTileFrames - 1) / kSiTileFrames;
+    tiles += (t + plan->tile_frames - 1) / plan->tile_frames;
   }
   frame_off[n_utts] = rows;
   *n_tiles = tiles;
@@ -543,12 +543,12 @@ extern "C" int pds_si_fill_tiles(const pds_si_plan* plan, int64_t n_utts, const 
   int64_t n = 0;
   for (int64_t u = 0; u < n_utts; ++u) {
     const int64_t t_total = frame_off[u + 1] - frame_off[u];
-    for (int64_t t0 = 0; t0 < t_total; t0 += kSiTileFrames) {
+    for (int64_t t0 = 0; t0 < t_total; t0 += plan->tile_frames) {
       pds_tile& tile = tiles[n++];
       tile.sig_off = sig_off[u];
       tile.sig_len = (int32_t)sig_len[u];
       tile.start = (int32_t)(plan->frame_start + t0 * plan->S);
-      tile.nframes = (int32_t)std::min<int64_t>(kSiTileFrames, t_total - t0);
+      tile.nframes = (int32_t)std::min<int64_t>(plan->tile_frames, t_total - t0);
       tile.utt = (int32_t)u;
       tile.out_row = frame_off[u] + t0;
     }
@@ -563,9 +563,7 @@ extern "C" int pds_si_run(pds_si_plan* plan, const float* d_signal, const pds_ti
   PDS_REQUIRE(d_signal && d_tiles && d_out && n_tiles > 0, "null buffer");
   SiParams p = plan->params;
   p.sig = d_signal, p.tiles = d_tiles, p.n_tiles = n_tiles, p.out = d_out;
-  // PDS_SI_KERNEL=direct forces the time-domain kernel (A/B runs, tests)
-  const char* force = getenv("PDS_SI_KERNEL");
-  if (plan->fft && !(force && force[0] == 'd')) {
+  if (plan->fft) {
     const int grid = (int)std::min<int64_t>(n_tiles, plan->fft_grid_limit);
     if (plan->power)
       si_fft_kernel<true><<<grid, kSiFftThreads, plan->fft_smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
