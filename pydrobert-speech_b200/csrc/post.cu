@@ -113,6 +113,104 @@ __global__ void __launch_bounds__(kDeltaThreads) deltas_kernel(const __grid_cons
   }
 }
 
+// Specialisation for the default Deltas(num_deltas=2, context_window=2): filters of 5 and 9 taps.
+// Same staging; then every thread owns one column of eight consecutive rows and slides the 16
+// staged values it needs through registers (taps in registers too): 16 shared-memory loads and
+// 112 FMAs for 24 outputs instead of one clamped load per tap.  Groups that touch an utterance
+// boundary take the clamped per-tap path.
+constexpr int kD25Rows = 8;
+__global__ void __launch_bounds__(kDeltaThreads) deltas25_kernel(const __grid_constant__ DeltaParams p) {
+  extern __shared__ __align__(16) float s_rows[];  // (R + 8) x cols | lo[R] | hi[R]
+  const int tid = threadIdx.x;
+  const int R = p.rows_per_cta, cols = p.cols;
+  constexpr int H = 4;
+  const long long r0 = (long long)blockIdx.x * R;
+  const int nrows = (int)min((long long)R, p.total_rows - r0);
+  const int stage_rows = nrows + 2 * H;
+  int* s_lo = reinterpret_cast<int*>(s_rows + (R + 2 * H) * cols);
+  int* s_hi = s_lo + R;
+  if (tid < nrows) {
+    const long long r = r0 + tid;
+    long long lo = 0, hi = p.n_utts;  // largest u with row_off[u] <= r (skips empty utterances)
+    while (hi - lo > 1) {
+      const long long mid = (lo + hi) >> 1;
+      if (p.row_off[mid] <= r) lo = mid; else hi = mid;
+    }
+    s_lo[tid] = (int)(p.row_off[lo] - (r0 - H));
+    s_hi[tid] = (int)(p.row_off[lo + 1] - 1 - (r0 - H));
+  }
+  {
+    const long long first = r0 - H;
+    const int total = stage_rows * cols;
+    if (first >= 0 && first + stage_rows <= p.total_rows) {
+      const float* __restrict__ src = p.in + first * cols;  // one contiguous block
+      int i = tid;
+      for (; i + 3 * kDeltaThreads < total; i += 4 * kDeltaThreads) {
+        const float a = src[i], b = src[i + kDeltaThreads], c = src[i + 2 * kDeltaThreads],
+                    d = src[i + 3 * kDeltaThreads];
+        s_rows[i] = a, s_rows[i + kDeltaThreads] = b, s_rows[i + 2 * kDeltaThreads] = c,
+        s_rows[i + 3 * kDeltaThreads] = d;
+      }
+      for (; i < total; i += kDeltaThreads) s_rows[i] = src[i];
+    } else {
+      for (int i = tid; i < total; i += kDeltaThreads) {
+        const int sr = i / cols, c = i - sr * cols;
+        const long long r = max(0LL, min(p.total_rows - 1, first + sr));
+        s_rows[i] = p.in[r * cols + c];
+      }
+    }
+  }
+  float f1[5], f2[9];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) f1[j] = p.taps[p.filt_off[0] + j];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) f2[j] = p.taps[p.filt_off[1] + j];
+  __syncthreads();
+
+  const int out_cols = 3 * cols;
+  const int groups = (nrows + kD25Rows - 1) / kD25Rows;
+  for (int item = tid; item < groups * cols; item += kDeltaThreads) {
+    const int g = item / cols, c = item - g * cols;
+    const int row0 = g * kD25Rows;
+    const int last = min(row0 + kD25Rows, nrows) - 1;
+    float* __restrict__ dst = p.out + (r0 + row0) * out_cols + c;
+    // the group is interior when the first row's window starts and the last row's window ends
+    // inside their (common) utterance; staged index of local row lr is lr + H
+    const bool interior = s_lo[row0] <= row0 && s_hi[last] >= row0 + kD25Rows + 2 * H - 1 &&
+                          s_lo[last] == s_lo[row0];
+    if (interior) {
+      float v[kD25Rows + 2 * H];
+#pragma unroll
+      for (int i = 0; i < kD25Rows + 2 * H; ++i) v[i] = s_rows[(row0 + i) * cols + c];
+#pragma unroll
+      for (int q = 0; q < kD25Rows; ++q) {
+        float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) d1 = fmaf(f1[j], v[q + 2 + j], d1);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) d2 = fmaf(f2[j], v[q + j], d2);
+        if (row0 + q <= last) {
+          dst[q * out_cols] = v[q + H];
+          dst[q * out_cols + cols] = d1;
+          dst[q * out_cols + 2 * cols] = d2;
+        }
+      }
+    } else {
+      for (int q = 0; row0 + q <= last; ++q) {
+        const int lr = row0 + q, lo = s_lo[lr], hi = s_hi[lr], centre = lr + H;
+        float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) d1 = fmaf(f1[j], s_rows[max(lo, min(hi, centre + j - 2)) * cols + c], d1);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) d2 = fmaf(f2[j], s_rows[max(lo, min(hi, centre + j - 4)) * cols + c], d2);
+        dst[q * out_cols] = s_rows[centre * cols + c];
+        dst[q * out_cols + cols] = d1;
+        dst[q * out_cols + 2 * cols] = d2;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // CMVN statistics: per-column sum and sum of squares in float64 (post.py:175-191)
 // ------------------------------------------------------------------------------------------
@@ -261,9 +359,17 @@ extern "C" int pds_deltas(const float* d_in, float* d_out, int64_t total_rows, i
     set_error("deltas: a context of %d rows exceeds shared memory", p.half_max);
     return PDS_ERR_UNSUPPORTED;
   }
+  const long long grid_x = (total_rows + p.rows_per_cta - 1) / p.rows_per_cta;
+  if (orders == 2 && p.filt_len[0] == 5 && p.filt_len[1] == 9 && n_cols <= kDeltaMaxChunk) {
+    // default Deltas(2, context 2): register-sliding specialisation
+    if (smem > 48 * 1024)
+      PDS_CUDA_CHECK(cudaFuncSetAttribute(deltas25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    deltas25_kernel<<<(unsigned)grid_x, kDeltaThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    PDS_CUDA_CHECK(cudaGetLastError());
+    return PDS_OK;
+  }
   if (smem > 48 * 1024)
     PDS_CUDA_CHECK(cudaFuncSetAttribute(deltas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long grid_x = (total_rows + p.rows_per_cta - 1) / p.rows_per_cta;
   const int grid_y = (n_cols + p.chunk - 1) / p.chunk;
   PDS_REQUIRE(grid_y <= 65535, "too many columns (%d)", n_cols);
   deltas_kernel<<<dim3((unsigned)grid_x, (unsigned)grid_y), kDeltaThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
