@@ -156,6 +156,22 @@ int pds_cmvn_accumulate(const float* d_feats, int64_t n_rows, int32_t n_cols, do
 int pds_cmvn_apply(const float* d_feats, float* d_out, int64_t n_rows, int32_t n_cols,
                    const double* d_stats, int32_t norm_var, int32_t* d_zero_var, void* stream);
 
+/* Deltas followed by Standardize without materialising the deltas in between (the chain of
+ * BASELINE config 5: post.py:441-491 then post.py:160-305).  Both calls compute the
+ * (total_rows x 3*n_cols) Deltas output on the fly from d_in (total_rows x n_cols):
+ *   pds_deltas_cmvn_accumulate ADDS its column sums / sums of squares / row count to d_stats,
+ *   laid out (2 x (3*n_cols + 1)) like pds_cmvn_accumulate;
+ *   pds_deltas_cmvn_apply writes the normalised output to d_out (total_rows x 3*n_cols).
+ * Implemented for the default Deltas(num_deltas=2, context_window=2) filters (5 and 9 taps) and
+ * n_cols <= 256; anything else returns PDS_ERR_UNSUPPORTED (use pds_deltas + pds_cmvn_*). */
+int pds_deltas_cmvn_accumulate(const float* d_in, int64_t total_rows, int32_t n_cols, int64_t n_utts,
+                               const int64_t* d_row_off, int32_t orders, const float* h_filters,
+                               const int32_t* h_filter_len, double* d_stats, void* stream);
+int pds_deltas_cmvn_apply(const float* d_in, float* d_out, int64_t total_rows, int32_t n_cols,
+                          int64_t n_utts, const int64_t* d_row_off, int32_t orders,
+                          const float* h_filters, const int32_t* h_filter_len, const double* d_stats,
+                          int32_t norm_var, int32_t* d_zero_var, void* stream);
+
 /* ------------------------------------------------------------------------------------------ *
  * Short-integration frame computer (compute.py:613-999; spec tests/test_compute.py:129-176)   *
  * ------------------------------------------------------------------------------------------ */

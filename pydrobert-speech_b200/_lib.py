@@ -168,6 +168,16 @@ _SIGNATURES = {
             _vp,
         ],
     ),
+    "pds_deltas_cmvn_accumulate": (
+        ctypes.c_int,
+        [_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, _vp, ctypes.c_int32, _c_float_p, _c_int32_p,
+         _vp, _vp],
+    ),
+    "pds_deltas_cmvn_apply": (
+        ctypes.c_int,
+        [_vp, _vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, _vp, ctypes.c_int32, _c_float_p,
+         _c_int32_p, _vp, ctypes.c_int32, _vp, _vp],
+    ),
     "pds_cmvn_accumulate": (
         ctypes.c_int,
         [_vp, ctypes.c_int64, ctypes.c_int32, _vp, _vp],

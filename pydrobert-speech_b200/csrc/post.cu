@@ -35,6 +35,10 @@ struct DeltaParams {
   int filt_off[kDeltaMaxOrders];
   int filt_len[kDeltaMaxOrders];
   float taps[kDeltaMaxTaps];
+  // fused CMVN (deltas25_kernel modes 1 and 2): statistics of / normalisation by the OUTPUT columns
+  double* stats;           // (2, 3*cols + 1): accumulated (mode 1) or read (mode 2)
+  int norm_var;
+  int* zero_var;
 };
 
 // One CTA produces `rows_per_cta` consecutive rows of one column chunk: the rows plus a halo of
@@ -118,96 +122,161 @@ __global__ void __launch_bounds__(kDeltaThreads) deltas_kernel(const __grid_cons
 // staged values it needs through registers (taps in registers too): 16 shared-memory loads and
 // 112 FMAs for 24 outputs instead of one clamped load per tap.  Groups that touch an utterance
 // boundary take the clamped per-tap path.
+//   MODE 0: store the (rows x 3*cols) outputs                     (post.Deltas)
+//   MODE 1: do not store; add the outputs' per-column sum / sum of squares (float64) to `stats`
+//           (post.Standardize.accumulate on Deltas output without materialising it)
+//   MODE 2: store the outputs normalised with `stats`             (Deltas -> Standardize.apply)
+// Persistent grid; a thread keeps its column for the whole launch (tid = group * cols + column).
 constexpr int kD25Rows = 8;
+enum { kD25Store = 0, kD25Stats = 1, kD25Apply = 2 };
+
+template <int MODE>
 __global__ void __launch_bounds__(kDeltaThreads) deltas25_kernel(const __grid_constant__ DeltaParams p) {
-  extern __shared__ __align__(16) float s_rows[];  // (R + 8) x cols | lo[R] | hi[R]
+  extern __shared__ __align__(16) float s_rows[];  // (R + 8) x cols | lo[R] | hi[R] | scale, shift [3*cols]
   const int tid = threadIdx.x;
   const int R = p.rows_per_cta, cols = p.cols;
   constexpr int H = 4;
-  const long long r0 = (long long)blockIdx.x * R;
-  const int nrows = (int)min((long long)R, p.total_rows - r0);
-  const int stage_rows = nrows + 2 * H;
+  const int out_cols = 3 * cols;
   int* s_lo = reinterpret_cast<int*>(s_rows + (R + 2 * H) * cols);
   int* s_hi = s_lo + R;
-  if (tid < nrows) {
-    const long long r = r0 + tid;
-    long long lo = 0, hi = p.n_utts;  // largest u with row_off[u] <= r (skips empty utterances)
-    while (hi - lo > 1) {
-      const long long mid = (lo + hi) >> 1;
-      if (p.row_off[mid] <= r) lo = mid; else hi = mid;
-    }
-    s_lo[tid] = (int)(p.row_off[lo] - (r0 - H));
-    s_hi[tid] = (int)(p.row_off[lo + 1] - 1 - (r0 - H));
-  }
-  {
-    const long long first = r0 - H;
-    const int total = stage_rows * cols;
-    if (first >= 0 && first + stage_rows <= p.total_rows) {
-      const float* __restrict__ src = p.in + first * cols;  // one contiguous block
-      int i = tid;
-      for (; i + 3 * kDeltaThreads < total; i += 4 * kDeltaThreads) {
-        const float a = src[i], b = src[i + kDeltaThreads], c = src[i + 2 * kDeltaThreads],
-                    d = src[i + 3 * kDeltaThreads];
-        s_rows[i] = a, s_rows[i + kDeltaThreads] = b, s_rows[i + 2 * kDeltaThreads] = c,
-        s_rows[i + 3 * kDeltaThreads] = d;
-      }
-      for (; i < total; i += kDeltaThreads) s_rows[i] = src[i];
-    } else {
-      for (int i = tid; i < total; i += kDeltaThreads) {
-        const int sr = i / cols, c = i - sr * cols;
-        const long long r = max(0LL, min(p.total_rows - 1, first + sr));
-        s_rows[i] = p.in[r * cols + c];
-      }
-    }
-  }
+  float* s_scale = reinterpret_cast<float*>(s_hi + R);
+  float* s_shift = s_scale + out_cols;
   float f1[5], f2[9];
 #pragma unroll
   for (int j = 0; j < 5; ++j) f1[j] = p.taps[p.filt_off[0] + j];
 #pragma unroll
   for (int j = 0; j < 9; ++j) f2[j] = p.taps[p.filt_off[1] + j];
-  __syncthreads();
+  if (MODE == kD25Apply) {  // scale / shift of every output column (post.py:264-294)
+    const double count = p.stats[out_cols];
+    for (int c = tid; c < out_cols; c += kDeltaThreads) {
+      const double mean = p.stats[c] / count;
+      double scale = 1.0;
+      if (p.norm_var) {
+        double var = p.stats[out_cols + 1 + c] / count - mean * mean;
+        if (fabs(var) <= 1e-8) {  // np.isclose(var, 0)
+          var = 1.0;
+          if (p.zero_var) *p.zero_var = 1;
+        }
+        scale = 1.0 / sqrt(var);
+      }
+      s_scale[c] = (float)scale;
+      s_shift[c] = (float)(mean * scale);
+    }
+  }
+  const int G = kDeltaThreads / cols;            // row groups in flight per pass
+  const int g0 = tid / cols, c = tid - g0 * cols;  // this thread's column never changes
+  const bool worker = g0 < G;
+  double sum[3] = {0.0, 0.0, 0.0}, sq[3] = {0.0, 0.0, 0.0};
+  const long long nblocks = (p.total_rows + R - 1) / R;
 
-  const int out_cols = 3 * cols;
-  const int groups = (nrows + kD25Rows - 1) / kD25Rows;
-  for (int item = tid; item < groups * cols; item += kDeltaThreads) {
-    const int g = item / cols, c = item - g * cols;
-    const int row0 = g * kD25Rows;
-    const int last = min(row0 + kD25Rows, nrows) - 1;
-    float* __restrict__ dst = p.out + (r0 + row0) * out_cols + c;
-    // the group is interior when the first row's window starts and the last row's window ends
-    // inside their (common) utterance; staged index of local row lr is lr + H
-    const bool interior = s_lo[row0] <= row0 && s_hi[last] >= row0 + kD25Rows + 2 * H - 1 &&
-                          s_lo[last] == s_lo[row0];
-    if (interior) {
+  for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const long long r0 = blk * R;
+    const int nrows = (int)min((long long)R, p.total_rows - r0);
+    const int stage_rows = nrows + 2 * H;
+    __syncthreads();  // the previous block's rows are no longer needed
+    if (tid < nrows) {
+      const long long r = r0 + tid;
+      long long lo = 0, hi = p.n_utts;  // largest u with row_off[u] <= r (skips empty utterances)
+      while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (p.row_off[mid] <= r) lo = mid; else hi = mid;
+      }
+      s_lo[tid] = (int)(p.row_off[lo] - (r0 - H));
+      s_hi[tid] = (int)(p.row_off[lo + 1] - 1 - (r0 - H));
+    }
+    {
+      const long long first = r0 - H;
+      const int total = stage_rows * cols;
+      if (first >= 0 && first + stage_rows <= p.total_rows) {
+        const float* __restrict__ src = p.in + first * cols;  // one contiguous block
+        int i = tid;
+        for (; i + 3 * kDeltaThreads < total; i += 4 * kDeltaThreads) {
+          const float a = src[i], b = src[i + kDeltaThreads], cc = src[i + 2 * kDeltaThreads],
+                      d = src[i + 3 * kDeltaThreads];
+          s_rows[i] = a, s_rows[i + kDeltaThreads] = b, s_rows[i + 2 * kDeltaThreads] = cc,
+          s_rows[i + 3 * kDeltaThreads] = d;
+        }
+        for (; i < total; i += kDeltaThreads) s_rows[i] = src[i];
+      } else {
+        for (int i = tid; i < total; i += kDeltaThreads) {
+          const int sr = i / cols, cc = i - sr * cols;
+          const long long r = max(0LL, min(p.total_rows - 1, first + sr));
+          s_rows[i] = p.in[r * cols + cc];
+        }
+      }
+    }
+    __syncthreads();
+    if (!worker) continue;
+    const int groups = (nrows + kD25Rows - 1) / kD25Rows;
+    for (int g = g0; g < groups; g += G) {
+      const int row0 = g * kD25Rows;
+      const int last = min(row0 + kD25Rows, nrows) - 1;
+      float* __restrict__ dst = p.out + (r0 + row0) * out_cols + c;
+      // the group is interior when the first row's window starts and the last row's window ends
+      // inside their (common) utterance; staged index of local row lr is lr + H
+      const bool interior = s_lo[row0] <= row0 && s_hi[last] >= row0 + kD25Rows + 2 * H - 1 &&
+                            s_lo[last] == s_lo[row0];
       float v[kD25Rows + 2 * H];
+      if (interior) {
 #pragma unroll
-      for (int i = 0; i < kD25Rows + 2 * H; ++i) v[i] = s_rows[(row0 + i) * cols + c];
+        for (int i = 0; i < kD25Rows + 2 * H; ++i) v[i] = s_rows[(row0 + i) * cols + c];
+      }
 #pragma unroll
       for (int q = 0; q < kD25Rows; ++q) {
-        float d1 = 0.f, d2 = 0.f;
+        if (row0 + q > last) break;
+        float d0, d1 = 0.f, d2 = 0.f;
+        if (interior) {
+          d0 = v[q + H];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) d1 = fmaf(f1[j], v[q + 2 + j], d1);
+          for (int j = 0; j < 5; ++j) d1 = fmaf(f1[j], v[q + 2 + j], d1);
 #pragma unroll
-        for (int j = 0; j < 9; ++j) d2 = fmaf(f2[j], v[q + j], d2);
-        if (row0 + q <= last) {
-          dst[q * out_cols] = v[q + H];
+          for (int j = 0; j < 9; ++j) d2 = fmaf(f2[j], v[q + j], d2);
+        } else {
+          const int lr = row0 + q, lo = s_lo[lr], hi = s_hi[lr], centre = lr + H;
+          d0 = s_rows[centre * cols + c];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) d1 = fmaf(f1[j], s_rows[max(lo, min(hi, centre + j - 2)) * cols + c], d1);
+#pragma unroll
+          for (int j = 0; j < 9; ++j) d2 = fmaf(f2[j], s_rows[max(lo, min(hi, centre + j - 4)) * cols + c], d2);
+        }
+        if (MODE == kD25Stats) {
+          sum[0] += (double)d0, sq[0] += (double)d0 * d0;
+          sum[1] += (double)d1, sq[1] += (double)d1 * d1;
+          sum[2] += (double)d2, sq[2] += (double)d2 * d2;
+        } else if (MODE == kD25Apply) {
+          dst[q * out_cols] = fmaf(d0, s_scale[c], -s_shift[c]);
+          dst[q * out_cols + cols] = fmaf(d1, s_scale[cols + c], -s_shift[cols + c]);
+          dst[q * out_cols + 2 * cols] = fmaf(d2, s_scale[2 * cols + c], -s_shift[2 * cols + c]);
+        } else {
+          dst[q * out_cols] = d0;
           dst[q * out_cols + cols] = d1;
           dst[q * out_cols + 2 * cols] = d2;
         }
       }
-    } else {
-      for (int q = 0; row0 + q <= last; ++q) {
-        const int lr = row0 + q, lo = s_lo[lr], hi = s_hi[lr], centre = lr + H;
-        float d1 = 0.f, d2 = 0.f;
+    }
+  }
+  if (MODE == kD25Stats) {
+    // fold the row groups of a column through shared memory, then one atomic per column and CTA
+    __syncthreads();
+    double* s_red = reinterpret_cast<double*>(s_rows);  // [G][6][cols]
+    if (worker) {
 #pragma unroll
-        for (int j = 0; j < 5; ++j) d1 = fmaf(f1[j], s_rows[max(lo, min(hi, centre + j - 2)) * cols + c], d1);
-#pragma unroll
-        for (int j = 0; j < 9; ++j) d2 = fmaf(f2[j], s_rows[max(lo, min(hi, centre + j - 4)) * cols + c], d2);
-        dst[q * out_cols] = s_rows[centre * cols + c];
-        dst[q * out_cols + cols] = d1;
-        dst[q * out_cols + 2 * cols] = d2;
+      for (int k = 0; k < 3; ++k) {
+        s_red[(g0 * 6 + k) * cols + c] = sum[k];
+        s_red[(g0 * 6 + 3 + k) * cols + c] = sq[k];
       }
     }
+    __syncthreads();
+    if (worker && g0 == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double a = 0.0, b = 0.0;
+        for (int g = 0; g < G; ++g) a += s_red[(g * 6 + k) * cols + c], b += s_red[(g * 6 + 3 + k) * cols + c];
+        atomicAdd(p.stats + k * cols + c, a);
+        atomicAdd(p.stats + (out_cols + 1) + k * cols + c, b);
+      }
+    }
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(p.stats + out_cols, (double)p.total_rows);
   }
 }
 
@@ -325,17 +394,20 @@ __global__ void __launch_bounds__(256)
 
 using namespace pds;
 
-extern "C" int pds_deltas(const float* d_in, float* d_out, int64_t total_rows, int32_t n_cols,
-                          int64_t n_utts, const int64_t* d_row_off, int32_t orders,
-                          const float* h_filters, const int32_t* h_filter_len, void* stream) {
+namespace {
+// shared by pds_deltas / pds_deltas_cmvn_accumulate / pds_deltas_cmvn_apply
+int run_deltas(int mode, const float* d_in, float* d_out, int64_t total_rows, int32_t n_cols, int64_t n_utts,
+               const int64_t* d_row_off, int32_t orders, const float* h_filters, const int32_t* h_filter_len,
+               double* d_stats, int32_t norm_var, int32_t* d_zero_var, void* stream) {
   PDS_REQUIRE(total_rows >= 0 && n_cols >= 1 && n_utts >= 0 && orders >= 0, "bad shape");
   if (total_rows == 0) return PDS_OK;
-  PDS_REQUIRE(d_in && d_out && d_row_off && n_utts >= 1, "null buffer");
+  PDS_REQUIRE(d_in && (d_out || mode == kD25Stats) && d_row_off && n_utts >= 1, "null buffer");
   PDS_REQUIRE(orders <= kDeltaMaxOrders, "at most %d delta orders are supported", kDeltaMaxOrders);
   PDS_REQUIRE(orders == 0 || (h_filters && h_filter_len), "null filter table");
   DeltaParams p;
   p.in = d_in, p.out = d_out, p.row_off = reinterpret_cast<const long long*>(d_row_off);
   p.total_rows = total_rows, p.n_utts = n_utts, p.cols = n_cols, p.orders = orders, p.half_max = 0;
+  p.stats = d_stats, p.norm_var = norm_var, p.zero_var = d_zero_var;
   int at = 0;
   for (int k = 0; k < orders; ++k) {
     const int len = h_filter_len[k];
@@ -353,20 +425,35 @@ extern "C" int pds_deltas(const float* d_in, float* d_out, int64_t total_rows, i
   p.chunk = std::min<int>(n_cols, kDeltaMaxChunk);
   const int budget_rows = (64 * 1024) / (int)(sizeof(float) * p.chunk) - 2 * p.half_max;
   p.rows_per_cta = std::max(8, std::min(kDeltaMaxRows, budget_rows));
-  const size_t smem = sizeof(float) * (size_t)(p.rows_per_cta + 2 * p.half_max) * p.chunk +
-                      2 * sizeof(int) * p.rows_per_cta;
+  size_t smem = sizeof(float) * (size_t)(p.rows_per_cta + 2 * p.half_max) * p.chunk +
+                2 * sizeof(int) * p.rows_per_cta;
   if (smem > 200 * 1024) {
     set_error("deltas: a context of %d rows exceeds shared memory", p.half_max);
     return PDS_ERR_UNSUPPORTED;
   }
   const long long grid_x = (total_rows + p.rows_per_cta - 1) / p.rows_per_cta;
-  if (orders == 2 && p.filt_len[0] == 5 && p.filt_len[1] == 9 && n_cols <= kDeltaMaxChunk) {
-    // default Deltas(2, context 2): register-sliding specialisation
-    if (smem > 48 * 1024)
-      PDS_CUDA_CHECK(cudaFuncSetAttribute(deltas25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    deltas25_kernel<<<(unsigned)grid_x, kDeltaThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  const bool fast = orders == 2 && p.filt_len[0] == 5 && p.filt_len[1] == 9 && n_cols <= kDeltaMaxChunk;
+  if (fast) {
+    // default Deltas(2, context 2): register-sliding specialisation, persistent grid
+    int device = 0;
+    PDS_CUDA_CHECK(cudaGetDevice(&device));
+    smem += 2 * sizeof(float) * 3 * (size_t)n_cols;                                     // scale | shift
+    smem = std::max(smem, sizeof(double) * 6 * (size_t)(kDeltaThreads / n_cols) * n_cols + 16);  // statistics fold
+    const void* fn = mode == kD25Stats   ? reinterpret_cast<const void*>(deltas25_kernel<kD25Stats>)
+                     : mode == kD25Apply ? reinterpret_cast<const void*>(deltas25_kernel<kD25Apply>)
+                                         : reinterpret_cast<const void*>(deltas25_kernel<kD25Store>);
+    if (smem > 48 * 1024) PDS_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::min<long long>(grid_x, (long long)sm_count(device) * 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mode == kD25Stats) deltas25_kernel<kD25Stats><<<grid, kDeltaThreads, smem, st>>>(p);
+    else if (mode == kD25Apply) deltas25_kernel<kD25Apply><<<grid, kDeltaThreads, smem, st>>>(p);
+    else deltas25_kernel<kD25Store><<<grid, kDeltaThreads, smem, st>>>(p);
     PDS_CUDA_CHECK(cudaGetLastError());
     return PDS_OK;
+  }
+  if (mode != kD25Store) {
+    set_error("fused Deltas + CMVN covers Deltas(num_deltas=2, context_window=2) only; materialise the deltas first");
+    return PDS_ERR_UNSUPPORTED;
   }
   if (smem > 48 * 1024)
     PDS_CUDA_CHECK(cudaFuncSetAttribute(deltas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -375,6 +462,31 @@ extern "C" int pds_deltas(const float* d_in, float* d_out, int64_t total_rows, i
   deltas_kernel<<<dim3((unsigned)grid_x, (unsigned)grid_y), kDeltaThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
   PDS_CUDA_CHECK(cudaGetLastError());
   return PDS_OK;
+}
+}  // namespace
+
+extern "C" int pds_deltas(const float* d_in, float* d_out, int64_t total_rows, int32_t n_cols,
+                          int64_t n_utts, const int64_t* d_row_off, int32_t orders,
+                          const float* h_filters, const int32_t* h_filter_len, void* stream) {
+  return run_deltas(kD25Store, d_in, d_out, total_rows, n_cols, n_utts, d_row_off, orders, h_filters,
+                    h_filter_len, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int pds_deltas_cmvn_accumulate(const float* d_in, int64_t total_rows, int32_t n_cols, int64_t n_utts,
+                                          const int64_t* d_row_off, int32_t orders, const float* h_filters,
+                                          const int32_t* h_filter_len, double* d_stats, void* stream) {
+  PDS_REQUIRE(d_stats, "null statistics buffer");
+  return run_deltas(kD25Stats, d_in, nullptr, total_rows, n_cols, n_utts, d_row_off, orders, h_filters,
+                    h_filter_len, d_stats, 0, nullptr, stream);
+}
+
+extern "C" int pds_deltas_cmvn_apply(const float* d_in, float* d_out, int64_t total_rows, int32_t n_cols,
+                                     int64_t n_utts, const int64_t* d_row_off, int32_t orders,
+                                     const float* h_filters, const int32_t* h_filter_len, const double* d_stats,
+                                     int32_t norm_var, int32_t* d_zero_var, void* stream) {
+  PDS_REQUIRE(d_stats, "null statistics buffer");
+  return run_deltas(kD25Apply, d_in, d_out, total_rows, n_cols, n_utts, d_row_off, orders, h_filters,
+                    h_filter_len, const_cast<double*>(d_stats), norm_var, d_zero_var, stream);
 }
 
 extern "C" int pds_cmvn_accumulate(const float* d_feats, int64_t n_rows, int32_t n_cols,

@@ -128,15 +128,28 @@ class FeaturePipeline:
         else:
             feats, frame_off = computer.compute_packed_device(d_signal, offsets, lengths)
         if self._device_post and feats.shape[0]:
-            row_off = None
-            for p in self._device_post:
-                if isinstance(p, Deltas):
-                    if row_off is None:
-                        row_off = torch.from_numpy(frame_off).to(feats.device)
-                    feats = p.apply_device(feats, row_off)
-                else:
-                    feats = p.apply_device(feats, out=feats)
+            feats = self._apply_device_post(feats, frame_off)
         return feats, frame_off
+
+    def _apply_device_post(self, feats, frame_off):
+        """Device-resident post-processors; Deltas directly followed by Standardize runs as one
+        fused pass (the deltas are never written un-normalised)"""
+        import torch
+
+        row_off = None
+        chain = list(self._device_post)
+        while chain:
+            p = chain.pop(0)
+            if isinstance(p, Deltas):
+                if row_off is None:
+                    row_off = torch.from_numpy(np.ascontiguousarray(frame_off)).to(feats.device)
+                if chain and isinstance(chain[0], Standardize):
+                    feats = chain.pop(0).apply_device(p.lazy_device(feats, row_off))
+                else:
+                    feats = p.apply_device(feats, row_off)
+            else:
+                feats = p.apply_device(feats, out=feats)
+        return feats
 
     # ---- host in, host out, pipelined ----------------------------------------------------
     def _chunks(self, lengths: np.ndarray) -> List[Tuple[int, int]]:
@@ -297,14 +310,7 @@ class FeaturePipeline:
             in_free[slot] = torch.cuda.Event()
             in_free[slot].record(compute)
             if self._device_post and rows:
-                row_off = None
-                for p in self._device_post:
-                    if isinstance(p, Deltas):
-                        if row_off is None:
-                            row_off = torch.from_numpy(layout.frame_off).to(device)
-                        feats = p.apply_device(feats, row_off)
-                    else:
-                        feats = p.apply_device(feats, out=feats)
+                feats = self._apply_device_post(feats, layout.frame_off)
             done = torch.cuda.Event()
             done.record(compute)
             with torch.cuda.stream(copy_out):

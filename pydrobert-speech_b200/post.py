@@ -131,6 +131,15 @@ class Standardize(PostProcessor):
         if rows == 0:
             raise ValueError("Cannot accumulate from empty array")
         self._check_width(cols)
+        if isinstance(feats, LazyDeltas):
+            # Deltas -> Standardize: statistics straight from the static features, the deltas are
+            # recomputed on the fly instead of being written and read back
+            d_stats = torch.zeros((2, cols + 1), dtype=torch.float64, device=feats.device)
+            if feats.fused_call("pds_deltas_cmvn_accumulate", d_stats.data_ptr()):
+                partial = d_stats.cpu().numpy()
+                self._stats = partial if self._stats is None else self._stats + partial
+                return
+            feats = feats.materialize()
         feats = feats.contiguous()
         d_stats = torch.zeros((2, cols + 1), dtype=torch.float64, device=feats.device)
         with torch.cuda.device(feats.device):
@@ -150,6 +159,17 @@ class Standardize(PostProcessor):
         self._check_width(cols)
         if not self.have_stats:
             raise ValueError("No stats have been accumulated")
+        if isinstance(feats, LazyDeltas):
+            d_stats = torch.from_numpy(np.ascontiguousarray(self._stats)).to(feats.device)
+            flag = torch.zeros(1, dtype=torch.int32, device=feats.device)
+            if out is None:
+                out = torch.empty((rows, cols), dtype=torch.float32, device=feats.device)
+            if feats.fused_call("pds_deltas_cmvn_apply", d_stats.data_ptr(), int(self._norm_var),
+                                flag.data_ptr(), out=out):
+                if self._norm_var and int(flag.item()):
+                    warnings.warn("0 variance encountered. Replacing with 1")
+                return out
+            feats = feats.materialize()
         feats = feats.contiguous()
         out = torch.empty_like(feats) if out is None else out
         d_stats = torch.from_numpy(np.ascontiguousarray(self._stats)).to(feats.device)
@@ -278,6 +298,13 @@ class Deltas(PostProcessor):
         for _ in range(num_deltas):
             self._filts.append(np.convolve(self._filts[-1], ramp))
 
+    def lazy_device(self, feats, row_off=None) -> "LazyDeltas":
+        """Like :meth:`apply_device`, but the output is only described, not computed: passing the
+        result to ``Standardize.accumulate_device`` / ``apply_device`` runs the fused
+        Deltas + CMVN kernels (``pds_deltas_cmvn_*``), which never write the un-normalised deltas.
+        ``materialize()`` gives the plain tensor."""
+        return LazyDeltas(self, feats, row_off)
+
     def apply_device(self, feats, row_off=None):
         """``(rows, C)`` float32 CUDA tensor -> ``(rows, C * (num_deltas + 1))``
 
@@ -366,3 +393,46 @@ class Stack(PostProcessor):
             index[time_axis] = slice(i, kept, self.num_vectors)
             groups.append(features[tuple(index)])
         return np.concatenate(groups, axis)
+
+
+class LazyDeltas:
+    """The not-yet-computed output of ``Deltas.apply_device(feats, row_off)`` (see
+    :meth:`Deltas.lazy_device`)"""
+
+    def __init__(self, deltas: "Deltas", feats, row_off=None):
+        import torch
+
+        self.deltas = deltas
+        self.feats = feats.contiguous()
+        rows = feats.shape[0]
+        self.row_off = (torch.tensor([0, rows], dtype=torch.int64, device=feats.device)
+                        if row_off is None else row_off)
+        self.device = feats.device
+        self.shape = (rows, feats.shape[1] * (deltas.num_deltas + 1))
+
+    def materialize(self):
+        return self.deltas.apply_device(self.feats, self.row_off)
+
+    def fused_call(self, name: str, *tail, out=None) -> bool:
+        """Run ``pds_deltas_cmvn_accumulate`` / ``_apply``; False if the filters are not covered"""
+        import ctypes
+
+        import torch
+
+        from ._gpu import stream_ptr
+        from ._lib import check, get_lib
+
+        d = self.deltas
+        taps = np.concatenate(d._filts[1:] + [np.zeros(0)]).astype(np.float32)
+        lens = np.array([len(f) for f in d._filts[1:]], dtype=np.int32)
+        rows, cols = self.feats.shape
+        head = [self.feats.data_ptr()] + ([out.data_ptr()] if out is not None else [])
+        args = head + [rows, cols, len(self.row_off) - 1, self.row_off.data_ptr(), d.num_deltas,
+                       taps.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                       lens.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))] + list(tail) + [stream_ptr(self.device)]
+        with torch.cuda.device(self.device):
+            rc = getattr(get_lib(), name)(*args)
+        if rc == -3:  # PDS_ERR_UNSUPPORTED: other filter lengths
+            return False
+        check(rc, name)
+        return True

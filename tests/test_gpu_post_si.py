@@ -157,6 +157,38 @@ def test_dither_kernel_statistics(speech):
     assert np.array_equal(out, speech.pre.Dither(2.0).apply(signal))
 
 
+def test_fused_deltas_cmvn_matches_separate_passes(speech):
+    """Deltas -> Standardize through the fused kernels (pds_deltas_cmvn_*): same statistics and
+    output as materialising the deltas first, across utterance boundaries; other filter lengths
+    fall back to the separate kernels"""
+    import torch
+
+    rng = np.random.default_rng(12)
+    dev = torch.device("cuda", 0)
+    lengths = [1, 3, 7, 8, 9, 130, 257, 1000, 2, 513]
+    feats = torch.from_numpy(rng.standard_normal((sum(lengths), 41)).astype(np.float32) * 3 + 1).to(dev)
+    row_off = torch.tensor(np.concatenate([[0], np.cumsum(lengths)]), dtype=torch.int64, device=dev)
+    for deltas in (speech.post.Deltas(2), speech.post.Deltas(1), speech.post.Deltas(2, context_window=3)):
+        full = deltas.apply_device(feats, row_off)
+        sep, fused = speech.post.Standardize(), speech.post.Standardize()
+        sep.accumulate_device(full)
+        fused.accumulate_device(deltas.lazy_device(feats, row_off))
+        assert np.allclose(sep._stats, fused._stats, rtol=1e-12, atol=1e-9)
+        want = sep.apply_device(full)
+        got = fused.apply_device(deltas.lazy_device(feats, row_off))
+        assert got.shape == want.shape
+        assert torch.allclose(got, want, rtol=1e-6, atol=1e-6)
+    # float64 reference of the whole chain on one utterance
+    one = feats[:777]
+    lazy = speech.post.Deltas(2).lazy_device(one)
+    cmvn = speech.post.Standardize()
+    cmvn.accumulate_device(lazy)
+    got = cmvn.apply_device(lazy).cpu().numpy().astype(np.float64)
+    ref = oracle.deltas(one.cpu().numpy().astype(np.float64), 2, 2)
+    ref = (ref - ref.mean(0)) / ref.std(0)
+    assert np.abs(got - ref).max() <= 2e-5
+
+
 # ---- short integration ------------------------------------------------------------------------
 @pytest.mark.parametrize("name", sorted(cases.SI_CASES))
 def test_si_matches_reference(speech, golden, name):
