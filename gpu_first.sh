@@ -1,7 +1,9 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_post_si.py tests/test_gpu_cli_torch.py -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --workload c5 > gpurun_out/bench_c5.json 2>gpurun_out/bench_c5.err; echo "c5 rc=$?"; python -c "
-import json; d=json.loads(open('gpurun_out/bench_c5.json').read().strip().splitlines()[-1]); print('c5', d['value'], d['ms_per_step'])"; tail -3 gpurun_out/bench_c5.err
+timeout 300 python -m pytest tests/test_gpu_stft.py -x -q -m gpu -k "(variants and (readme or kaldi or magnitude)) or edge or batch or int16 or preemph or dither or chunk or host" > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+for f in 2 1 2; do
+  PDS_TC_FRAMES=$f timeout 100 python tools/probe_stft.py 10000 > gpurun_out/probe_nf$f.log 2>&1; echo "probe NF=$f rc=$?"; tail -3 gpurun_out/probe_nf$f.log | head -2
+done
+timeout 300 ncu --metrics l1tex__t_sector_hit_rate.pct,gpu__time_duration.sum --clock-control none -k regex:stft_tc -s 3 -c 1 python tools/probe_stft.py 2000 2>&1 | grep -E "hit_rate|duration" 

@@ -443,6 +443,119 @@ __device__ __forceinline__ void fft_frame(const float* __restrict__ fx, const fl
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// NF frames at once on one sub-group of G lanes (stft_tc_kernel, R1 <= 16): the same transform as
+// fft_frame, with the twiddle tables in shared memory ([k][lane], conflict free) instead of 46
+// registers, so that a thread can carry two frames: two independent dependency chains per warp
+// hide the latency of the packed butterflies, and window / twiddle loads are shared by the frames.
+// The frames take turns in the sub-group's one exchange scratch.
+// ------------------------------------------------------------------------------------------
+template <int N, bool POWER, int MODE, int NF>
+__device__ __forceinline__ void fft_frames(const float* const (&fx)[NF], const float* __restrict__ s_w,
+                                           const float2* __restrict__ s_tws, const float2* __restrict__ s_twp,
+                                           float2* __restrict__ scr, float* const (&pcol)[NF],
+                                           float (&energy)[NF], int l, bool last_ok0, bool last_ok1,
+                                           bool want_energy, const StftParams& p) {
+  using Geo = FftGeom<N>;
+  constexpr int NC = Geo::NC, G = Geo::G, R1 = Geo::R1, NSUB = Geo::NSUB;
+  constexpr int TS = kTileStride;
+  constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
+  const int partner = (G - l) % G;
+  const cplx* wp = reinterpret_cast<const cplx*>(s_w) + l;
+  cplx z[NF][R1];
+  cplx energy2[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) energy2[f] = cmake(0.f, 0.f);
+  const cplx last_mask = cmake(last_ok0 ? 1.f : 0.f, last_ok1 ? 1.f : 0.f);
+#pragma unroll
+  for (int r = 0; r < R1; ++r) {
+    if (r < ROWS) {
+      const cplx w = wp[G * r];
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        cplx x = reinterpret_cast<const cplx*>(fx[f])[l + G * r];
+        z[f][r] = cmul2(x, w);  // window multiply: one FMUL2 per sample pair
+        if (MODE == kRowsAny) {
+          x = cmul2(x, cmake(2 * (G * r + l) < p.L ? 1.f : 0.f, 2 * (G * r + l) + 1 < p.L ? 1.f : 0.f));
+        } else if (r == ROWS - 1) {
+          x = cmul2(x, last_mask);
+        }
+        energy2[f] = cfma2(x, x, energy2[f]);
+      }
+    } else {
+#pragma unroll
+      for (int f = 0; f < NF; ++f) z[f][r] = cmake(0.f, 0.f);
+    }
+  }
+  if (want_energy) {
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      float e = cre(energy2[f]) + cim(energy2[f]);
+#pragma unroll
+      for (int off = G / 2; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off, G);
+      energy[f] = e;
+    }
+  }
+  constexpr unsigned ZROWS = ROWS >= R1 ? 0u : (zmask_full<R1>() & ~((1u << ROWS) - 1u));
+#pragma unroll
+  for (int f = 0; f < NF; ++f) Dft<R1, ZROWS>::run(z[f]);
+#pragma unroll
+  for (int k1 = 1; k1 < R1; ++k1) {
+    const float2 t = s_tws[k1 * G + l];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) z[f][k1] = cmul(z[f][k1], t);
+  }
+  cplx* cscr = reinterpret_cast<cplx*>(scr);
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) cscr[l * Geo::SCR_STRIDE + k1] = z[f][k1];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < NSUB; ++j) {
+      cplx v[G];
+#pragma unroll
+      for (int n2 = 0; n2 < G; ++n2) v[n2] = cscr[n2 * Geo::SCR_STRIDE + l + G * j];
+      Dft<G>::run(v);
+#pragma unroll
+      for (int k2 = 0; k2 < G; ++k2) z[f][j + NSUB * k2] = v[k2];
+    }
+    __syncwarp();
+  }
+  // real-FFT split: lane l pairs its lower-half registers with the partner's upper half
+#pragma unroll
+  for (int m = 0; m < R1 / 2; ++m) {
+    const float2 w = s_twp[m * G + l];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      cplx b;
+      b.v = __shfl_sync(0xffffffffu, z[f][R1 - 1 - m].v, partner, G);
+      if (l == 0) b = z[f][(R1 - m) % R1];
+      cplx xk, xq;
+      split_pair(z[f][m], b, w, xk, xq);
+      float pk = cnorm(xk), pq = cnorm(xq);
+      if (!POWER) {
+        pk = sqrtf(pk);
+        pq = sqrtf(pq);
+      }
+      const int k = l + G * m;
+      pcol[f][k * TS] = pk;
+      pcol[f][(NC - k) * TS] = pq;
+    }
+  }
+  if (l == 0) {  // bin NC/2 pairs with itself; its twiddle is -i
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const cplx a = z[f][R1 / 2];
+      cplx xk, xq;
+      split_pair(a, a, make_float2(0.f, -1.f), xk, xq);
+      float pk = cnorm(xk);
+      if (!POWER) pk = sqrtf(pk);
+      pcol[f][(NC / 2) * TS] = pk;
+    }
+  }
+}
+
 // shared-memory carve-up shared by host (size computation) and device
 struct SmemLayout {
   int x, w, scr, P, e, out, bar, desc, wt, total;  // offsets in floats; total in bytes
@@ -624,6 +737,13 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
 // from the accumulator fragments to global memory (floor, log, masked by nframes / F): no output
 // staging, no store phase.  The energy column is written by the fft phase.
 // ------------------------------------------------------------------------------------------
+// weight fragments are re-read by every tile: keep them in L1; outputs are written once: stream them
+__device__ __forceinline__ float4 ldg_keep(const float4* ptr) {
+  float4 v;
+  asm("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+  return v;
+}
+
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -646,9 +766,16 @@ struct TcSmem {
   static constexpr int oRaw = oCtl + 32;                                          // 2 raw tile descriptors
   static constexpr int oWstart = oRaw + 16;                                       // item ranges per warp
   static constexpr int oItems = oWstart + 12;                                     // bank work items (int4)
-  static constexpr int oX = oItems + 4 * kMaxItems;                               // samples [span_max + N]
+  static constexpr int oTws = oItems + 4 * kMaxItems;                             // W_NC^(lane*k1) at [k1][lane]
+  static constexpr int oTwp = oTws + 2 * Geo::R1 * Geo::G;                        // W_N^(lane+G*m) at [m][lane]
+  static constexpr int oX = oTwp + Geo::R1 * Geo::G;                              // samples [span_max + N]
   static_assert(oScr % 4 == 0 && oP % 4 == 0 && oBar % 4 == 0 && oItems % 4 == 0 && oX % 4 == 0, "16-byte regions");
-  static __host__ __device__ constexpr size_t bytes(int span_max) { return sizeof(float) * (size_t)(oX + span_max + N); }
+  // every frame reads up to N samples from its start (the window is zero past L), the span covers
+  // L of them: N - L (+ a vector of margin) floats of slack
+  static __host__ __device__ constexpr int x_floats(int span_max, int L) { return (span_max + (N - L) + 32 + 3) & ~3; }
+  static __host__ __device__ constexpr size_t bytes(int span_max, int L) {
+    return sizeof(float) * (size_t)(oX + x_floats(span_max, L));
+  }
 };
 
 // control block of a tile (ints): what every thread needs, prepared once by thread 0
@@ -745,7 +872,7 @@ __device__ __forceinline__ void bank_tc(int warp, int lane, const float* __restr
     do {
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-        const float4 f = __ldg(fr + 32 * s);
+        const float4 f = ldg_keep(fr + 32 * s);
         const float a[4] = {pa[(2 * s) * TS], pa[(2 * s) * TS + 8], pa[(2 * s + 1) * TS], pa[(2 * s + 1) * TS + 8]};
         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -772,24 +899,25 @@ __device__ __forceinline__ void bank_tc(int warp, int lane, const float* __restr
     float* __restrict__ r1 = r0 + 8 * C;
     const bool c0 = n0 + 2 * t < p.F, c1 = n0 + 2 * t + 1 < p.F;
     if (m0 + g < nframes) {
-      if (c0) r0[0] = v[0];
-      if (c1) r0[1] = v[1];
+      if (c0) __stcs(r0, v[0]);
+      if (c1) __stcs(r0 + 1, v[1]);
     }
     if (m0 + g + 8 < nframes) {
-      if (c0) r1[0] = v[2];
-      if (c1) r1[1] = v[3];
+      if (c0) __stcs(r1, v[2]);
+      if (c1) __stcs(r1 + 1, v[3]);
     }
   }
 }
 
-template <int N, bool POWER, typename T, int MODE>
+template <int N, bool POWER, typename T, int MODE, int NF>
 __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
     stft_tc_kernel(const __grid_constant__ StftParams p) {
   using Geo = FftGeom<N>;
   using Lay = TcSmem<N>;
   constexpr int G = Geo::G, R1 = Geo::R1;
   constexpr int FPR = kThreads / G;  // frames per round
-  constexpr bool REGTW = (R1 <= 16);
+  constexpr bool SMEMTW = NF > 1;    // twiddles in shared memory, NF frames per sub-group at once
+  constexpr bool REGTW = (R1 <= 16) && !SMEMTW;
   constexpr int TS = kTileStride;
   constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
 
@@ -813,7 +941,13 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
   for (int i = tid; i < p.tc_nitems; i += kThreads) s_items[i] = p.tc_items[i];
   if (tid <= kThreads / 32) s_wstart[tid] = p.tc_wstart[tid];
   for (int i = tid; i < Lay::kProws * TS; i += kThreads) s_P[i] = 0.f;  // incl. the padding rows
-  for (int i = tid; i < p.span_max + N; i += kThreads) s_x[i] = 0.f;    // slack must stay finite
+  for (int i = tid; i < Lay::x_floats(p.span_max, p.L); i += kThreads) s_x[i] = 0.f;  // slack must stay finite
+  float2* const s_tws = reinterpret_cast<float2*>(smem + Lay::oTws);
+  float2* const s_twp = reinterpret_cast<float2*>(smem + Lay::oTwp);
+  if (SMEMTW) {
+    for (int i = tid; i < R1 * G; i += kThreads) s_tws[i] = p.tw_stage[(i % G) * R1 + i / G];
+    for (int i = tid; i < (R1 / 2) * G; i += kThreads) s_twp[i] = p.tw_split[(i % G) * (R1 / 2) + i / G];
+  }
   int ti = blockIdx.x;
   if (tid == 0) {
     mbar_init(s_bar, 1);
@@ -881,17 +1015,49 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
     mbar_wait(s_bar, it & 1);
 
     // ---- fft phase ---------------------------------------------------------------------
-    for (int t0 = 0; t0 < nframes; t0 += FPR) {
+    if constexpr (SMEMTW) {
       // sub-groups past the end recompute the last frame (identical writes): full-warp shuffles
-      const int t = min(t0 + sub, nframes - 1);
-      float energy = 0.f;
-      fft_frame<N, POWER, MODE>(s_x + t * p.S, s_w, scr, s_P + t, &energy, tw_stage, tw_split, l, last_ok0,
-                                last_ok1, want_energy, p);
-      if (want_energy && l == 0) {  // energy column (compute.py:392-398); duplicates write equal values
-        float v = energy * p.inv_L;
-        if (!POWER) v = sqrtf(v);
-        if (p.use_log) v = fast_log(fmaxf(v, p.log_floor));
-        out_tile[t * p.C] = v;
+      if (nframes > FPR) {  // two frames per sub-group, FPR apart
+        const int ta = min(sub, nframes - 1), tb = min(sub + FPR, nframes - 1);
+        const float* const fx[2] = {s_x + ta * p.S, s_x + tb * p.S};
+        float* const pc[2] = {s_P + ta, s_P + tb};
+        float en[2] = {0.f, 0.f};
+        fft_frames<N, POWER, MODE, 2>(fx, s_w, s_tws, s_twp, scr, pc, en, l, last_ok0, last_ok1, want_energy, p);
+        if (want_energy && l == 0) {  // energy column (compute.py:392-398)
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            float v = en[f] * p.inv_L;
+            if (!POWER) v = sqrtf(v);
+            if (p.use_log) v = fast_log(fmaxf(v, p.log_floor));
+            __stcs(out_tile + (f ? tb : ta) * p.C, v);
+          }
+        }
+      } else {
+        const int ta = min(sub, nframes - 1);
+        const float* const fx[1] = {s_x + ta * p.S};
+        float* const pc[1] = {s_P + ta};
+        float en[1] = {0.f};
+        fft_frames<N, POWER, MODE, 1>(fx, s_w, s_tws, s_twp, scr, pc, en, l, last_ok0, last_ok1, want_energy, p);
+        if (want_energy && l == 0) {
+          float v = en[0] * p.inv_L;
+          if (!POWER) v = sqrtf(v);
+          if (p.use_log) v = fast_log(fmaxf(v, p.log_floor));
+          __stcs(out_tile + ta * p.C, v);
+        }
+      }
+    } else {
+      for (int t0 = 0; t0 < nframes; t0 += FPR) {
+        // sub-groups past the end recompute the last frame (identical writes): full-warp shuffles
+        const int t = min(t0 + sub, nframes - 1);
+        float energy = 0.f;
+        fft_frame<N, POWER, MODE>(s_x + t * p.S, s_w, scr, s_P + t, &energy, tw_stage, tw_split, l, last_ok0,
+                                  last_ok1, want_energy, p);
+        if (want_energy && l == 0) {  // energy column (compute.py:392-398); duplicates write equal values
+          float v = energy * p.inv_L;
+          if (!POWER) v = sqrtf(v);
+          if (p.use_log) v = fast_log(fmaxf(v, p.log_floor));
+          out_tile[t * p.C] = v;
+        }
       }
     }
     __syncthreads();  // s_x is free again, s_P is complete, the next control block is visible
@@ -1306,10 +1472,24 @@ KernelFn pick_fused(bool power, int dtype, int mode) {
   }
 }
 
+// frames per sub-group and pass: 2 where the registers allow it (R1 <= 16), see fft_frames
+template <int N>
+constexpr int tc_frames() {
+  return FftGeom<N>::R1 <= 16 ? 2 : 1;
+}
+
 template <int N, int MODE>
 KernelFn pick_tc_mode(bool power, int dtype) {
-  if (power) return dtype == PDS_I16 ? stft_tc_kernel<N, true, short, MODE> : stft_tc_kernel<N, true, float, MODE>;
-  return dtype == PDS_I16 ? stft_tc_kernel<N, false, short, MODE> : stft_tc_kernel<N, false, float, MODE>;
+  constexpr int NF = tc_frames<N>();
+#ifdef PDS_TC_AB
+  static const bool single = getenv("PDS_TC_FRAMES") && getenv("PDS_TC_FRAMES")[0] == '1';
+  if (single) {
+    if (power) return dtype == PDS_I16 ? stft_tc_kernel<N, true, short, MODE, 1> : stft_tc_kernel<N, true, float, MODE, 1>;
+    return dtype == PDS_I16 ? stft_tc_kernel<N, false, short, MODE, 1> : stft_tc_kernel<N, false, float, MODE, 1>;
+  }
+#endif
+  if (power) return dtype == PDS_I16 ? stft_tc_kernel<N, true, short, MODE, NF> : stft_tc_kernel<N, true, float, MODE, NF>;
+  return dtype == PDS_I16 ? stft_tc_kernel<N, false, short, MODE, NF> : stft_tc_kernel<N, false, float, MODE, NF>;
 }
 
 template <int N>
@@ -1548,10 +1728,10 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       size_t tc_bytes = 0;
       int tc_rows_max = 0, tc_items_max = 0;
       switch (N) {
-        case 256: tc_bytes = TcSmem<256>::bytes(p.span_max), tc_rows_max = TcSmem<256>::kProws, tc_items_max = TcSmem<256>::kMaxItems; break;
-        case 512: tc_bytes = TcSmem<512>::bytes(p.span_max), tc_rows_max = TcSmem<512>::kProws, tc_items_max = TcSmem<512>::kMaxItems; break;
-        case 1024: tc_bytes = TcSmem<1024>::bytes(p.span_max), tc_rows_max = TcSmem<1024>::kProws, tc_items_max = TcSmem<1024>::kMaxItems; break;
-        default: tc_bytes = TcSmem<2048>::bytes(p.span_max), tc_rows_max = TcSmem<2048>::kProws, tc_items_max = TcSmem<2048>::kMaxItems; break;
+        case 256: tc_bytes = TcSmem<256>::bytes(p.span_max, L), tc_rows_max = TcSmem<256>::kProws, tc_items_max = TcSmem<256>::kMaxItems; break;
+        case 512: tc_bytes = TcSmem<512>::bytes(p.span_max, L), tc_rows_max = TcSmem<512>::kProws, tc_items_max = TcSmem<512>::kMaxItems; break;
+        case 1024: tc_bytes = TcSmem<1024>::bytes(p.span_max, L), tc_rows_max = TcSmem<1024>::kProws, tc_items_max = TcSmem<1024>::kMaxItems; break;
+        default: tc_bytes = TcSmem<2048>::bytes(p.span_max, L), tc_rows_max = TcSmem<2048>::kProws, tc_items_max = TcSmem<2048>::kMaxItems; break;
       }
       plan->tc = tc_bytes <= smem_cap && F < 65536 && tc_p_rows <= tc_rows_max && tc_nitems <= tc_items_max;
       plan->tc_smem_bytes = tc_bytes;
