@@ -443,7 +443,10 @@ int run_deltas(int mode, const float* d_in, float* d_out, int64_t total_rows, in
                      : mode == kD25Apply ? reinterpret_cast<const void*>(deltas25_kernel<kD25Apply>)
                                          : reinterpret_cast<const void*>(deltas25_kernel<kD25Store>);
     if (smem > 48 * 1024) PDS_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)std::min<long long>(grid_x, (long long)sm_count(device) * 8);
+    // the statistics mode keeps its sums in registers across row blocks (persistent grid, one
+    // atomic per column and CTA); the store modes run one CTA per row block, which measured faster
+    const unsigned grid = mode == kD25Stats ? (unsigned)std::min<long long>(grid_x, (long long)sm_count(device) * 8)
+                                            : (unsigned)grid_x;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (mode == kD25Stats) deltas25_kernel<kD25Stats><<<grid, kDeltaThreads, smem, st>>>(p);
     else if (mode == kD25Apply) deltas25_kernel<kD25Apply><<<grid, kDeltaThreads, smem, st>>>(p);

@@ -1432,6 +1432,7 @@ struct pds_stft_plan {
   bool fast = false;
   bool ws = false;  // warp-specialised kernel available (N = 512 geometry, plain float32 input)
   size_t ws_smem_bytes = 0;
+  bool fused = false;  // scalar-bank kernel compiled for this size (N = 512 only: A/B runs, > 96 work items)
   bool tc = false;  // tensor-core bank kernel available (the default fast path)
   size_t tc_smem_bytes = 0;
   int tc_grid_limit = 0;
@@ -1535,15 +1536,8 @@ KernelFn pick_ws(bool power, int mode) {
 
 KernelFn pick_kernel(const pds_stft_plan* plan, int dtype) {
   if (plan->fast) {
-    switch (plan->N) {
-#ifndef PDS_DEV_N512_ONLY
-      case 256: return pick_fused<256>(plan->power, dtype, plan->row_mode);
-      case 1024: return pick_fused<1024>(plan->power, dtype, plan->row_mode);
-      case 2048: return pick_fused<2048>(plan->power, dtype, plan->row_mode);
-#endif
-      case 512: return pick_fused<512>(plan->power, dtype, plan->row_mode);
-      default: return nullptr;
-    }
+    // the scalar-bank kernel is instantiated for N = 512 only; other sizes run stft_tc_kernel
+    return plan->fused ? pick_fused<512>(plan->power, dtype, plan->row_mode) : nullptr;
   }
   if (plan->power) return dtype == PDS_I16 ? stft_direct_kernel<true, short> : stft_direct_kernel<true, float>;
   return dtype == PDS_I16 ? stft_direct_kernel<false, short> : stft_direct_kernel<false, float>;
@@ -1723,8 +1717,8 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     const SmemLayout without = fused_layout(N, G, R1, p.span_max, p_rows, npairs, plan->C, 0);
     p.weights_in_smem = (size_t)with.total <= std::min<size_t>(smem_cap, 110 * 1024) ? 1 : 0;
     plan->smem_bytes = p.weights_in_smem ? with.total : without.total;
-    if (plan->smem_bytes > smem_cap) plan->fast = false;  // huge frame shift: use the direct kernel
-    if (plan->fast) {
+    plan->fused = N == 512 && plan->smem_bytes <= smem_cap;
+    {
       size_t tc_bytes = 0;
       int tc_rows_max = 0, tc_items_max = 0;
       switch (N) {
@@ -1735,9 +1729,9 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       }
       plan->tc = tc_bytes <= smem_cap && F < 65536 && tc_p_rows <= tc_rows_max && tc_nitems <= tc_items_max;
       plan->tc_smem_bytes = tc_bytes;
-
     }
-    if (plan->fast && N == 512 && d->preemph == 0.f && d->dither == 0.f) {
+    if (!plan->fused && !plan->tc) plan->fast = false;  // huge frame shift / dft_size 2048: direct kernel
+    if (plan->fast && plan->fused && d->preemph == 0.f && d->dither == 0.f) {
       const WsLayout ws = ws_layout(N, G, R1, p.span_max, p_rows, npairs, plan->C, pair_total);
       plan->ws = (size_t)ws.total <= smem_cap;
       plan->ws_smem_bytes = ws.total;
@@ -1850,6 +1844,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   // opt in to the dynamic shared memory for every instantiation this plan may launch
   for (int dt = 0; dt < 2; ++dt) {
     KernelFn fn = pick_kernel(plan, dt);
+    if (!fn) continue;  // tensor-core kernel only
     err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn),
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
     if (err != cudaSuccess) {
@@ -1878,8 +1873,9 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   }
   plan->num_sms = prop.multiProcessorCount;
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(pick_kernel(plan, PDS_F32)),
-                                                plan->fast ? kThreads : kDirectThreads, plan->smem_bytes);
+  if (pick_kernel(plan, PDS_F32))
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(pick_kernel(plan, PDS_F32)),
+                                                  plan->fast ? kThreads : kDirectThreads, plan->smem_bytes);
   plan->grid_limit = prop.multiProcessorCount * std::max(1, occ);
   if (plan->tc) {
     int occ_tc = 1;
@@ -1997,13 +1993,14 @@ extern "C" int pds_stft_run(pds_stft_plan* plan, const void* d_signal, int sig_d
   }
   // PDS_STFT_KERNEL=scalar falls back to the CUDA-core bank kernel (A/B runs, tests)
   const bool want_scalar = force && force[0] == 's';
-  if (plan->tc && !want_scalar) {
+  if (plan->tc && !(want_scalar && plan->fused)) {
     const int grid = (int)std::min<int64_t>(n_tiles, plan->tc_grid_limit);
     pick_tc(plan, sig_dtype)<<<grid, kThreads, plan->tc_smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
     PDS_CUDA_CHECK(cudaGetLastError());
     return PDS_OK;
   }
   KernelFn fn = pick_kernel(plan, sig_dtype);
+  PDS_REQUIRE(fn, "no kernel for this plan");
   const int grid = (int)std::min<int64_t>(n_tiles, plan->grid_limit);
   const int threads = plan->fast ? kThreads : kDirectThreads;
   fn<<<grid, threads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
