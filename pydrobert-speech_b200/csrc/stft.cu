@@ -1685,9 +1685,13 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       per_warp[w].push_back(i);
       load[w] += runs[i].nblk + 2;  // +2: per-item prologue / epilogue
     }
+    // warp 0 also prepares the next tile and issues its TMA copy: give it the lightest share
+    std::vector<int> by_load(n_warps);
+    for (int w = 0; w < n_warps; ++w) by_load[w] = w;
+    std::stable_sort(by_load.begin(), by_load.end(), [&](int a, int b) { return load[a] < load[b]; });
     for (int w = 0; w < n_warps; ++w) {
       tc_wstart[w] = (int)(tc_items.size() / 4);
-      for (int i : per_warp[w]) {
+      for (int i : per_warp[by_load[w]]) {
         const Run& r = runs[i];
         tc_items.push_back(r.n0 | (r.slot << 16));
         tc_items.push_back(r.blk0);
