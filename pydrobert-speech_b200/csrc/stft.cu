@@ -176,19 +176,26 @@ __device__ __forceinline__ void stage_vec4(float* __restrict__ s_x, const T* __r
 
 // fused dither (pre.py:90-104), four samples per Philox call: groups are aligned to the
 // utterance-relative sample index (the key of the random stream), so loads are per element
-template <typename T, int THREADS, bool PRE>
+template <typename T, int THREADS, bool PRE, bool DITHER_FIRST>
 __device__ __forceinline__ void stage_dither4(float* __restrict__ s_x, const T* __restrict__ src, long long first,
                                               int j0, int nvec, float c, float d, uint64_t seed, int utt,
                                               int tid) {
   for (int v = tid; v < nvec; v += THREADS) {
     const int j = j0 + 4 * v;
+    const uint64_t group = (uint64_t)(first + j) >> 2;
     float x0 = (float)src[j], x1 = (float)src[j + 1], x2 = (float)src[j + 2], x3 = (float)src[j + 3];
-    if (PRE) {  // pre-emphasis first, then dither
-      const float prev = (float)src[j - 1];
-      x3 -= c * x2, x2 -= c * x1, x1 -= c * x0, x0 -= c * prev;
+    const float4 n = philox_normal4(seed, utt, group);
+    if (PRE && DITHER_FIRST) {  // y[i] = (x[i] + d n[i]) - c (x[i-1] + d n[i-1])
+      const float prev = fmaf(d, philox_normal4(seed, utt, group - 1).w, (float)src[j - 1]);
+      x0 = fmaf(d, n.x, x0), x1 = fmaf(d, n.y, x1), x2 = fmaf(d, n.z, x2), x3 = fmaf(d, n.w, x3);
+      s_x[j] = x0 - c * prev, s_x[j + 1] = x1 - c * x0, s_x[j + 2] = x2 - c * x1, s_x[j + 3] = x3 - c * x2;
+    } else {
+      if (PRE) {  // pre-emphasis first, then dither
+        const float prev = (float)src[j - 1];
+        x3 -= c * x2, x2 -= c * x1, x1 -= c * x0, x0 -= c * prev;
+      }
+      s_x[j] = fmaf(d, n.x, x0), s_x[j + 1] = fmaf(d, n.y, x1), s_x[j + 2] = fmaf(d, n.z, x2), s_x[j + 3] = fmaf(d, n.w, x3);
     }
-    const float4 n = philox_normal4(seed, utt, (uint64_t)(first + j) >> 2);
-    s_x[j] = fmaf(d, n.x, x0), s_x[j + 1] = fmaf(d, n.y, x1), s_x[j + 2] = fmaf(d, n.z, x2), s_x[j + 3] = fmaf(d, n.w, x3);
   }
 }
 
@@ -204,18 +211,19 @@ __device__ __forceinline__ void stage_samples_slow(float* __restrict__ s_x, cons
   // numbers: the in-range middle is converted / filtered four samples at a time with aligned
   // vector loads; only the reflected ends and a few unaligned samples go through the per-element
   // path below.  (pre.py:136-149: y[0] = x[0], y[i] = x[i] - c x[i-1], applied before framing.)
-  if (p.dither != 0.f && a1 == a0 && (p.preemph == 0.f || !p.dither_first)) {
+  if (p.dither != 0.f && a1 == a0) {
     const float c = p.preemph;
     int r0 = (int)max(0LL, -first);
-    if (c != 0.f && first + r0 == 0) ++r0;
+    if (c != 0.f) r0 = max(r0, (int)min((long long)span, 4 - first));  // groups 1.. only: sample 0 and its group go per element
     const int r1 = (int)min((long long)span, (long long)tile.sig_len - first);
     if (r1 - r0 >= 64) {
       const T* __restrict__ src = sig + tile.sig_off + first;
       const int j0 = r0 + (int)((4 - ((first + r0) & 3)) & 3);  // first + j0 is a multiple of 4
       const int nvec = (r1 - j0) >> 2;
       const int j1 = j0 + 4 * nvec;
-      if (c != 0.f) stage_dither4<T, THREADS, true>(s_x, src, first, j0, nvec, c, p.dither, p.seed, tile.utt, tid);
-      else stage_dither4<T, THREADS, false>(s_x, src, first, j0, nvec, c, p.dither, p.seed, tile.utt, tid);
+      if (c == 0.f) stage_dither4<T, THREADS, false, false>(s_x, src, first, j0, nvec, c, p.dither, p.seed, tile.utt, tid);
+      else if (p.dither_first) stage_dither4<T, THREADS, true, true>(s_x, src, first, j0, nvec, c, p.dither, p.seed, tile.utt, tid);
+      else stage_dither4<T, THREADS, true, false>(s_x, src, first, j0, nvec, c, p.dither, p.seed, tile.utt, tid);
       const int rest = j0 + (span - j1);
       for (int e = tid; e < rest; e += THREADS) {
         const int at = e < j0 ? e : e - j0 + j1;

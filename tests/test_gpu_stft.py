@@ -118,6 +118,38 @@ def test_fused_dither_statistics(speech):
     assert np.array_equal(feats, again) and not np.array_equal(feats, other)
 
 
+@pytest.mark.parametrize("order", ["dither", "dither_preemph", "preemph_dither"])
+def test_fused_preprocessing_matches_standalone_passes(speech, order):
+    """The vectorised staging paths (four samples per Philox call, aligned vector loads, reflected
+    edges per element) against the stand-alone pds_dither / pds_preemphasize passes followed by the
+    plain kernel: same random stream (seed, utterance, sample), same features"""
+    import torch
+
+    from pydrobert_speech_b200.pre import _launch_rows, _rows_on_device
+
+    rng = np.random.default_rng(21)
+    computer = build(speech, cases.README_FBANK)
+    for n in (201, 403, 4000, 16001, 33333):
+        sig = (rng.standard_normal(n) * 100).astype(np.float32)
+        device, d_in, offsets, lengths, _ = _rows_on_device(sig, None)
+        seed = 1234
+        if order == "dither":
+            d_pre = _launch_rows("pds_dither", d_in, offsets, lengths, device, 2.0, seed)
+            kwargs = dict(dither=2.0)
+        elif order == "dither_preemph":
+            d_pre = _launch_rows("pds_dither", d_in, offsets, lengths, device, 2.0, seed)
+            d_pre = _launch_rows("pds_preemphasize", d_pre, offsets, lengths, device, 0.97)
+            kwargs = dict(dither=2.0, preemph=0.97, dither_first=True)
+        else:
+            d_pre = _launch_rows("pds_preemphasize", d_in, offsets, lengths, device, 0.97)
+            d_pre = _launch_rows("pds_dither", d_pre, offsets, lengths, device, 2.0, seed)
+            kwargs = dict(dither=2.0, preemph=0.97, dither_first=False)
+        want = computer.compute_batch([d_pre.cpu().numpy()])[0]
+        got = computer.compute_batch([sig], seed=seed, **kwargs)[0]
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 2e-4
+
+
 def test_chunked_equals_full(speech):
     rng = np.random.default_rng(7)
     for cfg in (cases.README_FBANK, cases.KALDI_FBANK, cases.GAMMATONE_64):

@@ -35,7 +35,9 @@ for name, sig, out in (("float32", d_f32, feats_a), ("int16", d_i16, feats_b)):
         best = min(best, t0.elapsed_time(t1))
     print(f"{name}: {best:.3f} ms  frames/s={layout.rows / (best * 1e-3):.3e}")
 for name, kw in (("float32 + preemph 0.97", dict(preemph=0.97)), ("float32 + dither 1.0", dict(dither=1.0)),
-                 ("int16 + preemph 0.97", dict(preemph=0.97))):
+                 ("int16 + preemph 0.97", dict(preemph=0.97)),
+                 ("float32 + dither, then preemph", dict(dither=1.0, preemph=0.97, dither_first=True)),
+                 ("float32 + preemph, then dither", dict(dither=1.0, preemph=0.97, dither_first=False))):
     sig = d_i16 if name.startswith("int16") else d_f32
     for _ in range(3):
         computer.run_batch(layout, sig, out=feats_b, **kw)
