@@ -110,7 +110,8 @@ int pds_stft_fill_tiles_range(const pds_stft_plan* plan, int64_t sig_off, int64_
                               int64_t buf_origin, int64_t first_frame, int64_t nframes,
                               int64_t out_row, pds_tile* h_tiles, int64_t* n_tiles);
 
-/* Enqueue the fused kernel.  d_out is (total_frames x num_coeffs) float32, row-major. */
+/* Enqueue the fused kernel.  d_out is (total_frames x num_coeffs) float32, row-major; d_tiles
+ * must be 16-byte aligned (descriptors are prefetched with 16-byte asynchronous copies). */
 int pds_stft_run(pds_stft_plan* plan, const void* d_signal, int sig_dtype, const pds_tile* d_tiles,
                  int64_t n_tiles, float* d_out, uint64_t seed, void* stream);
 
