@@ -924,8 +924,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
   using Lay = TcSmem<N>;
   constexpr int G = Geo::G, R1 = Geo::R1;
   constexpr int FPR = kThreads / G;  // frames per round
-  constexpr bool SMEMTW = NF > 1;    // twiddles in shared memory, NF frames per sub-group at once
-  constexpr bool REGTW = (R1 <= 16) && !SMEMTW;
+  // twiddles live in shared memory ([k][lane]); NF frames per sub-group at once (see fft_frames)
   constexpr int TS = kTileStride;
   constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
 
@@ -952,10 +951,8 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
   for (int i = tid; i < Lay::x_floats(p.span_max, p.L); i += kThreads) s_x[i] = 0.f;  // slack must stay finite
   float2* const s_tws = reinterpret_cast<float2*>(smem + Lay::oTws);
   float2* const s_twp = reinterpret_cast<float2*>(smem + Lay::oTwp);
-  if (SMEMTW) {
-    for (int i = tid; i < R1 * G; i += kThreads) s_tws[i] = p.tw_stage[(i % G) * R1 + i / G];
-    for (int i = tid; i < (R1 / 2) * G; i += kThreads) s_twp[i] = p.tw_split[(i % G) * (R1 / 2) + i / G];
-  }
+  for (int i = tid; i < R1 * G; i += kThreads) s_tws[i] = p.tw_stage[(i % G) * R1 + i / G];
+  for (int i = tid; i < (R1 / 2) * G; i += kThreads) s_twp[i] = p.tw_split[(i % G) * (R1 / 2) + i / G];
   int ti = blockIdx.x;
   if (tid == 0) {
     mbar_init(s_bar, 1);
@@ -972,13 +969,6 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
     }
   }
 
-  float2 tw_stage[REGTW ? R1 : 1], tw_split[REGTW ? R1 / 2 : 1];
-  if (REGTW) {
-#pragma unroll
-    for (int k1 = 0; k1 < R1; ++k1) tw_stage[k1] = p.tw_stage[l * R1 + k1];
-#pragma unroll
-    for (int m = 0; m < R1 / 2; ++m) tw_split[m] = p.tw_split[l * (R1 / 2) + m];
-  }
   const bool last_ok0 = 2 * (G * (ROWS - 1) + l) < p.L;
   const bool last_ok1 = 2 * (G * (ROWS - 1) + l) + 1 < p.L;
   float2* const scr = s_scr + sub * Geo::SCR_FLOAT2;
@@ -1023,25 +1013,25 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
     mbar_wait(s_bar, it & 1);
 
     // ---- fft phase ---------------------------------------------------------------------
-    if constexpr (SMEMTW) {
-      // sub-groups past the end recompute the last frame (identical writes): full-warp shuffles
-      if (nframes > FPR) {  // two frames per sub-group, FPR apart
-        const int ta = min(sub, nframes - 1), tb = min(sub + FPR, nframes - 1);
-        const float* const fx[2] = {s_x + ta * p.S, s_x + tb * p.S};
-        float* const pc[2] = {s_P + ta, s_P + tb};
-        float en[2] = {0.f, 0.f};
-        fft_frames<N, POWER, MODE, 2>(fx, s_w, s_tws, s_twp, scr, pc, en, l, last_ok0, last_ok1, want_energy, p);
-        if (want_energy && l == 0) {  // energy column (compute.py:392-398)
+    // sub-groups past the end recompute the last frame (identical writes): full-warp shuffles
+    if (NF == 2 && nframes > FPR) {  // two frames per sub-group, FPR apart: the tile is one pass
+      const int ta = min(sub, nframes - 1), tb = min(sub + FPR, nframes - 1);
+      const float* const fx[2] = {s_x + ta * p.S, s_x + tb * p.S};
+      float* const pc[2] = {s_P + ta, s_P + tb};
+      float en[2] = {0.f, 0.f};
+      fft_frames<N, POWER, MODE, 2>(fx, s_w, s_tws, s_twp, scr, pc, en, l, last_ok0, last_ok1, want_energy, p);
+      if (want_energy && l == 0) {  // energy column (compute.py:392-398)
 #pragma unroll
-          for (int f = 0; f < 2; ++f) {
-            float v = en[f] * p.inv_L;
-            if (!POWER) v = sqrtf(v);
-            if (p.use_log) v = fast_log(fmaxf(v, p.log_floor));
-            __stcs(out_tile + (f ? tb : ta) * p.C, v);
-          }
+        for (int f = 0; f < 2; ++f) {
+          float v = en[f] * p.inv_L;
+          if (!POWER) v = sqrtf(v);
+          if (p.use_log) v = fast_log(fmaxf(v, p.log_floor));
+          __stcs(out_tile + (f ? tb : ta) * p.C, v);
         }
-      } else {
-        const int ta = min(sub, nframes - 1);
+      }
+    } else {
+      for (int t0 = 0; t0 < nframes; t0 += FPR) {
+        const int ta = min(t0 + sub, nframes - 1);
         const float* const fx[1] = {s_x + ta * p.S};
         float* const pc[1] = {s_P + ta};
         float en[1] = {0.f};
@@ -1051,20 +1041,6 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
           if (!POWER) v = sqrtf(v);
           if (p.use_log) v = fast_log(fmaxf(v, p.log_floor));
           __stcs(out_tile + ta * p.C, v);
-        }
-      }
-    } else {
-      for (int t0 = 0; t0 < nframes; t0 += FPR) {
-        // sub-groups past the end recompute the last frame (identical writes): full-warp shuffles
-        const int t = min(t0 + sub, nframes - 1);
-        float energy = 0.f;
-        fft_frame<N, POWER, MODE>(s_x + t * p.S, s_w, scr, s_P + t, &energy, tw_stage, tw_split, l, last_ok0,
-                                  last_ok1, want_energy, p);
-        if (want_energy && l == 0) {  // energy column (compute.py:392-398); duplicates write equal values
-          float v = energy * p.inv_L;
-          if (!POWER) v = sqrtf(v);
-          if (p.use_log) v = fast_log(fmaxf(v, p.log_floor));
-          out_tile[t * p.C] = v;
         }
       }
     }
@@ -1490,13 +1466,6 @@ constexpr int tc_frames() {
 template <int N, int MODE>
 KernelFn pick_tc_mode(bool power, int dtype) {
   constexpr int NF = tc_frames<N>();
-#ifdef PDS_TC_AB
-  static const bool single = getenv("PDS_TC_FRAMES") && getenv("PDS_TC_FRAMES")[0] == '1';
-  if (single) {
-    if (power) return dtype == PDS_I16 ? stft_tc_kernel<N, true, short, MODE, 1> : stft_tc_kernel<N, true, float, MODE, 1>;
-    return dtype == PDS_I16 ? stft_tc_kernel<N, false, short, MODE, 1> : stft_tc_kernel<N, false, float, MODE, 1>;
-  }
-#endif
   if (power) return dtype == PDS_I16 ? stft_tc_kernel<N, true, short, MODE, NF> : stft_tc_kernel<N, true, float, MODE, NF>;
   return dtype == PDS_I16 ? stft_tc_kernel<N, false, short, MODE, NF> : stft_tc_kernel<N, false, float, MODE, NF>;
 }
