@@ -458,6 +458,14 @@ __device__ __forceinline__ void fft_frame(const float* __restrict__ fx, const fl
 // hide the latency of the packed butterflies, and window / twiddle loads are shared by the frames.
 // The frames take turns in the sub-group's one exchange scratch.
 // ------------------------------------------------------------------------------------------
+// frames per tile and row stride of the power-spectrum tile (stride = 2 mod 16 keeps the fft-phase
+// writes and the A-fragment reads conflict free): 32 frames, 16 for the 1025-bin spectra of N = 2048
+template <int N>
+struct TcTile {
+  static constexpr int kFrames = N <= 1024 ? kTileFrames : 16;
+  static constexpr int kStride = kFrames + 2;
+};
+
 template <int N, bool POWER, int MODE, int NF>
 __device__ __forceinline__ void fft_frames(const float* const (&fx)[NF], const float* __restrict__ s_w,
                                            const float2* __restrict__ s_tws, const float2* __restrict__ s_twp,
@@ -466,7 +474,7 @@ __device__ __forceinline__ void fft_frames(const float* const (&fx)[NF], const f
                                            bool want_energy, const StftParams& p) {
   using Geo = FftGeom<N>;
   constexpr int NC = Geo::NC, G = Geo::G, R1 = Geo::R1, NSUB = Geo::NSUB;
-  constexpr int TS = kTileStride;
+  constexpr int TS = TcTile<N>::kStride;
   constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
   const int partner = (G - l) % G;
   const cplx* wp = reinterpret_cast<const cplx*>(s_w) + l;
@@ -769,7 +777,7 @@ struct TcSmem {
   static constexpr int oW = 0;                                                    // window [N]
   static constexpr int oScr = oW + N;                                             // fft exchange scratch
   static constexpr int oP = oScr + 2 * (kThreads / Geo::G) * Geo::SCR_FLOAT2;     // s_P [kProws][34]
-  static constexpr int oBar = oP + kProws * kTileStride;                          // mbarrier
+  static constexpr int oBar = oP + kProws * TcTile<N>::kStride;                    // mbarrier
   static constexpr int oCtl = oBar + 4;                                           // 2 control blocks x 16 ints
   static constexpr int oRaw = oCtl + 32;                                          // 2 raw tile descriptors
   static constexpr int oWstart = oRaw + 16;                                       // item ranges per warp
@@ -848,11 +856,11 @@ __device__ __forceinline__ void tc_issue(const StftParams& p, const int* __restr
   }
 }
 
+template <int TS>
 __device__ __forceinline__ void bank_tc(int warp, int lane, const float* __restrict__ s_P,
                                         const int4* __restrict__ s_items, const int* __restrict__ s_wstart,
                                         const float4* __restrict__ frags, const StftParams& p,
                                         float* __restrict__ out_tile, int nframes) {
-  constexpr int TS = kTileStride;
   const int g = lane >> 2, t = lane & 3;
   const bool use_log = p.use_log != 0;
   const float log_floor = p.log_floor;
@@ -925,7 +933,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
   constexpr int G = Geo::G, R1 = Geo::R1;
   constexpr int FPR = kThreads / G;  // frames per round
   // twiddles live in shared memory ([k][lane]); NF frames per sub-group at once (see fft_frames)
-  constexpr int TS = kTileStride;
+  constexpr int TS = TcTile<N>::kStride;
   constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
 
   extern __shared__ __align__(16) float smem[];
@@ -1050,7 +1058,7 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
     if (has_next && tid == 0) tc_issue<T>(p, cn, s_x, s_bar);
 
     // ---- filter bank on the tensor cores, results straight to global memory --------------
-    bank_tc(tid >> 5, tid & 31, s_P, s_items, s_wstart, p.tc_frags, p, out_tile, nframes);
+    bank_tc<TS>(tid >> 5, tid & 31, s_P, s_items, s_wstart, p.tc_frags, p, out_tile, nframes);
     if (has_next && (cn[kCtlFlags] & kFlagHandStaged))
       stage_samples_slow<T, kThreads>(s_x, p, tc_tile_of(cn), cn[kCtlSpan], cn[kCtlA0], cn[kCtlA1]);
     __syncthreads();  // s_P may be overwritten, hand-staged samples are visible
@@ -1646,7 +1654,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
             tc_frags.push_back(l0);
             tc_frags.push_back(l1);
           }
-      for (int m0 = 0; m0 < kTileFrames; m0 += 16) runs.push_back({8 * j, m0, blk0, nblk, frag});
+      for (int m0 = 0; m0 < (N > 1024 ? 16 : kTileFrames); m0 += 16) runs.push_back({8 * j, m0, blk0, nblk, frag});
       tc_p_rows = std::max(tc_p_rows, 16 * (blk0 + nblk));
     }
     // longest-processing-time-first deal to the warps
@@ -1692,7 +1700,8 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     plan->row_mode = rows == R1 ? kRows16 : (rows == (R1 * 13) / 16 ? kRows13 : kRowsAny);
     p.rows_full = L / (2 * G);
     p.row_partial = (L % (2 * G)) != 0;
-    p.span_max = (kTileFrames - 1) * S + L;
+    const int fast_tile_frames = N > 1024 ? 16 : kTileFrames;  // TcTile<N>::kFrames
+    p.span_max = (fast_tile_frames - 1) * S + L;
     // keep the weights in shared memory while that still leaves room for two CTAs per SM
     const SmemLayout with = fused_layout(N, G, R1, p.span_max, p_rows, npairs, plan->C, pair_total);
     const SmemLayout without = fused_layout(N, G, R1, p.span_max, p_rows, npairs, plan->C, 0);
@@ -1726,7 +1735,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       return PDS_ERR_UNSUPPORTED;
     }
   }
-  plan->tile_frames = plan->fast ? kTileFrames : kDirectTileFrames;
+  plan->tile_frames = plan->fast ? (N > 1024 ? 16 : kTileFrames) : kDirectTileFrames;
 
   // ---- build the constant tables on the host (double precision trig) --------------------
   std::vector<float> wt(std::max(wtotal, 4), 0.f);

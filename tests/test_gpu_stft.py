@@ -118,6 +118,28 @@ def test_fused_dither_statistics(speech):
     assert np.array_equal(feats, again) and not np.array_equal(feats, other)
 
 
+@pytest.mark.parametrize("frame_ms,shift_ms", [(64, 16), (100, 20), (70, 10)])
+def test_large_dft_sizes(speech, frame_ms, shift_ms):
+    """1024- and 2048-point transforms (long frames / high sampling rates): the tensor-core kernel
+    with 32- and 16-frame tiles against the oracle, ragged batch incl. utterance-edge tiles"""
+    cfg = dict(cases.README_FBANK, frame_length_ms=frame_ms, frame_shift_ms=shift_ms)
+    from pydrobert_speech_b200._gpu import current_device
+    from pydrobert_speech_b200._lib import get_lib
+
+    rng = np.random.default_rng(31)
+    computer = build(speech, cfg)
+    assert computer._dft_size in (1024, 2048)
+    plan = computer._plan(current_device())
+    assert get_lib().pds_stft_is_fast_path(plan.handle) == 1
+    lengths = [0, 700, 1601, 5000, 16000, 40001, computer.frame_shift * 33 + 7]
+    signals = [(rng.standard_normal(n) * 1000).astype(np.float32) for n in lengths]
+    for sig, got in zip(signals, computer.compute_batch(signals)):
+        want = oracle_feats(computer, sig.astype(np.float64))
+        assert got.shape == want.shape
+        if len(want):
+            assert np.abs(got - want).max() <= LOG_TOL
+
+
 @pytest.mark.parametrize("order", ["dither", "dither_preemph", "preemph_dither"])
 def test_fused_preprocessing_matches_standalone_passes(speech, order):
     """The vectorised staging paths (four samples per Philox call, aligned vector loads, reflected
