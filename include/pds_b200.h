@@ -91,7 +91,7 @@ void pds_stft_plan_destroy(pds_stft_plan* plan);
 int pds_stft_num_coeffs(const pds_stft_plan* plan);
 int pds_stft_tile_frames(const pds_stft_plan* plan);
 /* 1 if the plan runs the shared-memory FFT kernel, 0 if it runs the generic direct-DFT kernel
- * (non power-of-two dft_size, odd frame_shift, dft_size outside [64, 2048]). */
+ * (non power-of-two dft_size, dft_size outside [256, 2048]). */
 int pds_stft_is_fast_path(const pds_stft_plan* plan);
 
 /* Frame count of a signal: 0 if sig_len < L/2 + 1 else (sig_len + S/2) / S  (compute.py:580-596) */

@@ -17,7 +17,7 @@
 //             spectrum with the folded weights (compute.py:416-457), floor + log.
 //   store   : the (nframes x C) block is contiguous in the packed output; coalesced copy.
 //
-// Geometry outside the shared-memory FFT's reach (non power-of-two N, odd S, ...) runs through
+// Geometry outside the shared-memory FFT's reach (non power-of-two N, N < 256) runs through
 // stft_direct_kernel, a plain O(L*K) DFT per frame with the same staging and bank code.
 #include <algorithm>
 #include <cmath>
@@ -477,6 +477,7 @@ __device__ __forceinline__ void fft_frames(const float* const (&fx)[NF], const f
   constexpr int TS = TcTile<N>::kStride;
   constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
   const int partner = (G - l) % G;
+  const bool odd_shift = (p.S & 1) != 0;  // kernel-uniform
   const cplx* wp = reinterpret_cast<const cplx*>(s_w) + l;
   cplx z[NF][R1];
   cplx energy2[NF];
@@ -489,7 +490,14 @@ __device__ __forceinline__ void fft_frames(const float* const (&fx)[NF], const f
       const cplx w = wp[G * r];
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
-        cplx x = reinterpret_cast<const cplx*>(fx[f])[l + G * r];
+        cplx x;
+        if (MODE == kRowsAny && odd_shift) {  // odd frame shift (always the generic row mode): frames may
+                                              // start on an odd sample, no 8-byte loads
+          const float* q = fx[f] + 2 * (l + G * r);
+          x = cmake(q[0], q[1]);
+        } else {
+          x = reinterpret_cast<const cplx*>(fx[f])[l + G * r];
+        }
         z[f][r] = cmul2(x, w);  // window multiply: one FMUL2 per sample pair
         if (MODE == kRowsAny) {
           x = cmul2(x, cmake(2 * (G * r + l) < p.L ? 1.f : 0.f, 2 * (G * r + l) + 1 < p.L ? 1.f : 0.f));
@@ -1692,12 +1700,13 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   // ---- pick the kernel: shared-memory FFT when the geometry allows, else direct DFT ------
   StftParams& p = plan->params;
   const bool pow2 = (N & (N - 1)) == 0;
-  plan->fast = pow2 && N >= 256 && N <= 2048 && (S % 2 == 0);
+  plan->fast = pow2 && N >= 256 && N <= 2048;  // odd frame shifts: tensor-core kernel only
   if (plan->fast) {
     geometry_for(N, &plan->G, &plan->R1);
     const int G = plan->G, R1 = plan->R1;
     const int rows = (L + 2 * G - 1) / (2 * G);  // stage-1 rows that carry samples
     plan->row_mode = rows == R1 ? kRows16 : (rows == (R1 * 13) / 16 ? kRows13 : kRowsAny);
+    if (S % 2) plan->row_mode = kRowsAny;  // odd frame shift: the generic mode loads sample pairs with 4-byte loads
     p.rows_full = L / (2 * G);
     p.row_partial = (L % (2 * G)) != 0;
     const int fast_tile_frames = N > 1024 ? 16 : kTileFrames;  // TcTile<N>::kFrames
@@ -1707,7 +1716,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     const SmemLayout without = fused_layout(N, G, R1, p.span_max, p_rows, npairs, plan->C, 0);
     p.weights_in_smem = (size_t)with.total <= std::min<size_t>(smem_cap, 110 * 1024) ? 1 : 0;
     plan->smem_bytes = p.weights_in_smem ? with.total : without.total;
-    plan->fused = N == 512 && plan->smem_bytes <= smem_cap;
+    plan->fused = N == 512 && S % 2 == 0 && plan->smem_bytes <= smem_cap;
     {
       size_t tc_bytes = 0;
       int tc_rows_max = 0, tc_items_max = 0;

@@ -118,7 +118,7 @@ def test_fused_dither_statistics(speech):
     assert np.array_equal(feats, again) and not np.array_equal(feats, other)
 
 
-@pytest.mark.parametrize("frame_ms,shift_ms", [(64, 16), (100, 20), (70, 10)])
+@pytest.mark.parametrize("frame_ms,shift_ms", [(64, 16), (100, 20), (70, 10), (25, 10.0625), (68.875, 10.0625)])
 def test_large_dft_sizes(speech, frame_ms, shift_ms):
     """1024- and 2048-point transforms (long frames / high sampling rates): the tensor-core kernel
     with 32- and 16-frame tiles against the oracle, ragged batch incl. utterance-edge tiles"""
@@ -128,7 +128,7 @@ def test_large_dft_sizes(speech, frame_ms, shift_ms):
 
     rng = np.random.default_rng(31)
     computer = build(speech, cfg)
-    assert computer._dft_size in (1024, 2048)
+    assert computer._dft_size in (512, 1024, 2048)  # 10.0625 ms = 161 samples: odd frame shift
     plan = computer._plan(current_device())
     assert get_lib().pds_stft_is_fast_path(plan.handle) == 1
     lengths = [0, 700, 1601, 5000, 16000, 40001, computer.frame_shift * 33 + 7]
