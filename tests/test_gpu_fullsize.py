@@ -97,3 +97,36 @@ def test_post_chain_statistics_at_full_size(speech, corpus):
     separate = speech.post.Standardize()
     separate.accumulate_device(deltas.apply_device(feats, row_off))
     assert np.allclose(fused._stats, separate._stats, rtol=1e-11, atol=1e-6)
+
+
+def test_short_integration_on_long_utterances(speech):
+    """config 4 (SI + Gabor-41 with frame pooling) on long utterances (20 x 60 s + 2 x 600 s):
+    homogeneity of the pooled magnitude, independence of far-away samples, oracle on a prefix"""
+    import torch
+
+    from pydrobert_speech_b200.compute import PackedSignals
+
+    cfg = {"name": "si", "bank": {"name": "gabor", "scaling_function": "mel", "num_filts": 41}}
+    si = speech.alias_factory_subclass_from_arg(speech.compute.FrameComputer, cfg)
+    lengths = np.array([16000 * 60] * 20 + [16000 * 600] * 2, dtype=np.int64)
+    offsets, total = PackedSignals.layout(lengths, 0)
+    device = torch.device("cuda", 0)
+    gen = torch.Generator(device=device).manual_seed(7)
+    d_signal = torch.randn(total, device=device, generator=gen) * 1000.0
+    feats, frame_off = si.compute_packed_device(d_signal, offsets, lengths)
+    assert feats.shape == (int(frame_off[-1]), 41) and bool(torch.isfinite(feats).all())
+    assert int(frame_off[-1]) == sum(si.num_frames(int(n)) for n in lengths)
+    # log |y| pooled: feats(4x) = feats(x) + ln 4
+    scaled, _ = si.compute_packed_device(d_signal * 4.0, offsets, lengths)
+    assert float(((scaled - feats) - float(np.log(4.0))).abs().max()) <= 2e-5
+    # the first 2 s of a 600 s utterance: same frames as the prefix alone (away from its end) and
+    # within tolerance of the float64 oracle
+    u = 21
+    prefix = d_signal[int(offsets[u]) : int(offsets[u]) + 32000].cpu().numpy()
+    inside = feats[int(frame_off[u]) : int(frame_off[u]) + 190].cpu().numpy()
+    alone = si.compute_full(prefix)
+    assert np.allclose(inside, alone[:190], rtol=0, atol=2e-6)
+    want = oracle.si_features(
+        prefix.astype(np.float64), si._impulse_responses, si._window.reshape(-1), si.frame_shift,
+        si._zero_pad, si._pool_start, si._frames_lost, si._power, si._log)
+    assert np.abs(alone - want).max() <= LOG_TOL
