@@ -1994,6 +1994,7 @@ extern "C" int pds_stft_run(pds_stft_plan* plan, const void* d_signal, int sig_d
   const bool want_scalar = force && force[0] == 's';
   if (plan->tc && !(want_scalar && plan->fused)) {
     PDS_REQUIRE((reinterpret_cast<uintptr_t>(d_tiles) & 15u) == 0, "d_tiles must be 16-byte aligned");
+    PDS_REQUIRE(n_tiles < ((int64_t)1 << 30), "at most 2^30 tiles per launch (got %lld)", (long long)n_tiles);
     const int grid = (int)std::min<int64_t>(n_tiles, plan->tc_grid_limit);
     pick_tc(plan, sig_dtype)<<<grid, kThreads, plan->tc_smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
     PDS_CUDA_CHECK(cudaGetLastError());
