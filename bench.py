@@ -324,9 +324,9 @@ def run_ours(args, rank, local_rank, world):
     e2e = None
     if not args.no_e2e:
         pipeline = FeaturePipeline(computer, chunk_samples=args.chunk_samples)
-        host_sig = torch.empty(total, dtype=torch.float32).pin_memory()
+        host_sig = torch.empty(total, dtype=torch.float32, pin_memory=True)
         host_sig.copy_(d_signal)
-        host_out = torch.empty((frames, computer.num_coeffs), dtype=torch.float32).pin_memory()
+        host_out = torch.empty((frames, computer.num_coeffs), dtype=torch.float32, pin_memory=True)
         packed = PackedSignals(host_sig.numpy(), offsets, lengths)
         del d_signal, d_feats
         torch.cuda.empty_cache()
@@ -344,7 +344,7 @@ def run_ours(args, rank, local_rank, world):
         # supplementary: the same corpus as 16-bit PCM (what wav files hold): half the bytes over PCIe
         e2e_pcm = None
         if not args.no_pcm and world == 1:  # supplementary, single-GPU runs only (3.5 GB more pinned memory per rank)
-            host_pcm = torch.empty(total, dtype=torch.int16).pin_memory()
+            host_pcm = torch.empty(total, dtype=torch.int16, pin_memory=True)
             host_pcm.copy_(host_sig.clamp(-32768, 32767).round_().to(torch.int16))
             packed_pcm = PackedSignals(host_pcm.numpy(), offsets, lengths)
             pipeline.run_host(packed_pcm, out=host_out.numpy(), device=device)  # warm-up
