@@ -358,6 +358,27 @@ __global__ void __launch_bounds__(256)
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int c = (int)(i % cols);
   const int step = (int)(stride % cols);
+  // 16 bytes per thread and access when the buffers allow it: a quarter of the memory requests
+  if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(feats) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0) {
+    const long long total4 = total >> 2;
+    const int step4 = (int)((4 * stride) % cols);
+    int c0 = (int)((4 * i) % cols);
+    for (long long i4 = i; i4 < total4; i4 += stride) {
+      const float4 x = __ldcs(reinterpret_cast<const float4*>(feats) + i4);
+      int c1 = c0 + 1 == cols ? 0 : c0 + 1;
+      int c2 = c1 + 1 == cols ? 0 : c1 + 1;
+      int c3 = c2 + 1 == cols ? 0 : c2 + 1;
+      float4 y;
+      y.x = fmaf(x.x, s_scale[c0], -s_shift[c0]);
+      y.y = fmaf(x.y, s_scale[c1], -s_shift[c1]);
+      y.z = fmaf(x.z, s_scale[c2], -s_shift[c2]);
+      y.w = fmaf(x.w, s_scale[c3], -s_shift[c3]);
+      __stcs(reinterpret_cast<float4*>(out) + i4, y);
+      c0 += step4;
+      if (c0 >= cols) c0 -= cols;
+    }
+    return;
+  }
   for (; i < total; i += stride) {
     out[i] = fmaf(feats[i], s_scale[c], -s_shift[c]);
     c += step;
