@@ -327,6 +327,54 @@ __global__ void __launch_bounds__(kStatsThreadsX* kStatsThreadsY)
     atomicAdd(stats + cols, (double)n_rows);
 }
 
+// 16-byte variant: the matrix is read as a flat float4 stream.  With B threads per CTA such that
+// 4 * B is a multiple of `cols`, and CTA slabs that are multiples of B float4s, the four
+// (consecutive, wrapping) columns a thread sees never change: sums stay in registers (float64),
+// are folded through shared memory once per CTA, then one atomic per column and CTA.
+__global__ void __launch_bounds__(256)
+    cmvn_stats4_kernel(const float4* __restrict__ feats4, long long total4, long long slab, int cols, int B,
+                       long long n_rows, double* __restrict__ stats) {
+  extern __shared__ __align__(16) double s_fold[];  // sum[cols] | sq[cols]
+  const int t = threadIdx.x;
+  for (int i = t; i < 2 * cols; i += blockDim.x) s_fold[i] = 0.0;
+  __syncthreads();
+  if (t < B) {
+    const long long begin = (long long)blockIdx.x * slab, end = min(total4, begin + slab);
+    double sum[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
+    long long i = begin + t;
+    for (; i + 3LL * B < end; i += 4LL * B) {  // four independent 16-byte loads in flight
+      const float4 a = __ldcs(feats4 + i), b = __ldcs(feats4 + i + B), c = __ldcs(feats4 + i + 2LL * B),
+                   d = __ldcs(feats4 + i + 3LL * B);
+      sum[0] += ((double)a.x + (double)b.x) + ((double)c.x + (double)d.x);
+      sum[1] += ((double)a.y + (double)b.y) + ((double)c.y + (double)d.y);
+      sum[2] += ((double)a.z + (double)b.z) + ((double)c.z + (double)d.z);
+      sum[3] += ((double)a.w + (double)b.w) + ((double)c.w + (double)d.w);
+      sq[0] += ((double)a.x * a.x + (double)b.x * b.x) + ((double)c.x * c.x + (double)d.x * d.x);
+      sq[1] += ((double)a.y * a.y + (double)b.y * b.y) + ((double)c.y * c.y + (double)d.y * d.y);
+      sq[2] += ((double)a.z * a.z + (double)b.z * b.z) + ((double)c.z * c.z + (double)d.z * d.z);
+      sq[3] += ((double)a.w * a.w + (double)b.w * b.w) + ((double)c.w * c.w + (double)d.w * d.w);
+    }
+    for (; i < end; i += B) {
+      const float4 a = __ldcs(feats4 + i);
+      sum[0] += (double)a.x, sum[1] += (double)a.y, sum[2] += (double)a.z, sum[3] += (double)a.w;
+      sq[0] += (double)a.x * a.x, sq[1] += (double)a.y * a.y, sq[2] += (double)a.z * a.z, sq[3] += (double)a.w * a.w;
+    }
+    int c = (int)((4LL * t) % cols);  // 4 * begin is a multiple of cols
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(&s_fold[c], sum[k]);
+      atomicAdd(&s_fold[cols + c], sq[k]);
+      c = c + 1 == cols ? 0 : c + 1;
+    }
+  }
+  __syncthreads();
+  for (int c = t; c < cols; c += blockDim.x) {
+    atomicAdd(stats + c, s_fold[c]);
+    atomicAdd(stats + (cols + 1) + c, s_fold[cols + c]);
+  }
+  if (blockIdx.x == 0 && t == 0) atomicAdd(stats + cols, (double)n_rows);
+}
+
 // ------------------------------------------------------------------------------------------
 // CMVN apply: y = x * scale[c] - mean[c] * scale[c]  (post.py:264-294)
 // ------------------------------------------------------------------------------------------
@@ -520,6 +568,24 @@ extern "C" int pds_cmvn_accumulate(const float* d_feats, int64_t n_rows, int32_t
   PDS_REQUIRE(d_feats && d_stats, "null buffer");
   int device = 0;
   PDS_CUDA_CHECK(cudaGetDevice(&device));
+  {
+    // 16-byte path: needs a thread count B <= 256 with cols | 4B, an aligned buffer, whole float4s
+    int g = n_cols % 4 == 0 ? 4 : (n_cols % 2 == 0 ? 2 : 1);
+    const int unit = n_cols / g;  // B must be a multiple of this
+    const long long total = n_rows * (long long)n_cols;
+    if (unit <= 256 && (total & 3) == 0 && (reinterpret_cast<uintptr_t>(d_feats) & 15u) == 0) {
+      const int B = unit * (256 / unit);
+      const long long total4 = total >> 2;
+      long long ctas = std::min<long long>((long long)sm_count(device) * 8, (total4 + B - 1) / B);
+      long long slab = (total4 + ctas - 1) / ctas;
+      slab = (slab + B - 1) / B * B;
+      ctas = (total4 + slab - 1) / slab;
+      cmvn_stats4_kernel<<<(unsigned)ctas, 256, 2 * sizeof(double) * n_cols, static_cast<cudaStream_t>(stream)>>>(
+          reinterpret_cast<const float4*>(d_feats), total4, slab, n_cols, B, n_rows, d_stats);
+      PDS_CUDA_CHECK(cudaGetLastError());
+      return PDS_OK;
+    }
+  }
   const int stripes = (n_cols + kStatsThreadsX - 1) / kStatsThreadsX;
   // ~8 resident CTAs per SM in total, but never more slabs than there are row groups
   long long slabs = std::max(1, sm_count(device) * 8 / stripes);
