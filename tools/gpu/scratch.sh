@@ -1,7 +1,6 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu.log
-timeout 300 python tools/probe_other.py > gpurun_out/probe_other.log 2>&1; cat gpurun_out/probe_other.log
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --workload c5 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('c5', d['value'], d['ms_per_step'])"
+timeout 120 python tools/probe_si.py 0 > gpurun_out/plain_si.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:si_fft -s 2 -c 1 -o gpurun_out/prof_si_fft -f python tools/probe_si.py 0 > gpurun_out/ncu_si.log 2>&1
+echo "ncu rc=$?"; tail -1 gpurun_out/ncu_si.log; cat gpurun_out/plain_si.log
