@@ -20,6 +20,7 @@ There is no CPU implementation in this package.  A CPU restatement used for test
 """
 
 import abc
+import os
 
 from typing import List, Mapping, Optional, Sequence, Tuple, Union
 
@@ -351,7 +352,10 @@ class ShortTimeFourierTransformFrameComputer(LinearFilterBankFrameComputer):
 
         from ._lib import PdsStftDesc, check, get_lib
 
-        key = (device.index, float(preemph), float(dither), bool(dither_first))
+        # the kernel switch (read by the library once per plan) and the log floor are baked into a
+        # plan: both are part of the key, so changing either takes effect on the next call
+        key = (device.index, float(preemph), float(dither), bool(dither_first),
+               os.environ.get("PDS_STFT_KERNEL", ""), float(config.LOG_FLOOR_VALUE))
         plan = self._plans.get(key)
         if plan is not None:
             return plan

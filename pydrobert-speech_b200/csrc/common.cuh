@@ -32,6 +32,28 @@ void set_error(const char* fmt, ...);
     }                                 \
   } while (0)
 
+// Switches to `device` for the lifetime of the guard and restores the caller's current device
+// afterwards: the C ABI never leaves the calling thread on another GPU than it came with.
+class DeviceGuard {
+ public:
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev_) != cudaSuccess) prev_ = -1;
+    status_ = prev_ == device ? cudaSuccess : cudaSetDevice(device);
+    switched_ = status_ == cudaSuccess && prev_ != device;
+  }
+  ~DeviceGuard() {
+    if (switched_ && prev_ >= 0) cudaSetDevice(prev_);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+  cudaError_t status() const { return status_; }
+
+ private:
+  int prev_ = -1;
+  bool switched_ = false;
+  cudaError_t status_ = cudaSuccess;
+};
+
 // Number of SMs of the current device (cached per device).
 int sm_count(int device);
 

@@ -387,7 +387,8 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
     set_error("no usable CUDA device %d (found %d); this library has no CPU fallback", device, ndev);
     return PDS_ERR_CUDA;
   }
-  PDS_CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  PDS_CUDA_CHECK(guard.status());
   pds_si_plan* plan = new (std::nothrow) pds_si_plan();
   if (!plan) return PDS_ERR_NOMEM;
   plan->device = device;
@@ -507,7 +508,7 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
 
 extern "C" void pds_si_plan_destroy(pds_si_plan* plan) {
   if (!plan) return;
-  cudaSetDevice(plan->device);
+  DeviceGuard guard(plan->device);
   if (plan->d_blob) cudaFree(plan->d_blob);
   delete plan;
 }

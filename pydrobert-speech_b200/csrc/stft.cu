@@ -62,6 +62,8 @@ struct StftParams {
   const int* tc_wstart;
   const float4* tc_frags;
   int tc_nitems;
+  int w_probe;              // development probes of stft_w_kernel: 1 = no bank, 2 = no transform
+  int w_frag4;              // float4 entries of tc_frags (stft_w_kernel keeps them in shared memory)
   int tc_p_rows;            // rows of the power-spectrum tile the blocks may touch (multiple of 16)
   int weights_total;        // floats in `pair_weights`
   int weights_in_smem;
@@ -466,20 +468,19 @@ struct TcTile {
   static constexpr int kStride = kFrames + 2;
 };
 
-template <int N, bool POWER, int MODE, int NF>
-__device__ __forceinline__ void fft_frames(const float* const (&fx)[NF], const float* __restrict__ s_w,
-                                           const float2* __restrict__ s_tws, const float2* __restrict__ s_twp,
-                                           float2* __restrict__ scr, float* const (&pcol)[NF],
-                                           float (&energy)[NF], int l, bool last_ok0, bool last_ok1,
-                                           bool want_energy, const StftParams& p) {
+// first part of the transform (everything that does not touch the power-spectrum tile): window,
+// energy, R1-point DFT, twiddle, exchange through the sub-group's scratch, G-point DFT(s).  On
+// return lane l holds Z[k] for k = l (mod G) in z[f][(k - l) / G].
+template <int N, int MODE, int NF>
+__device__ __forceinline__ void fft_front(const float* const (&fx)[NF], const float* __restrict__ s_w,
+                                          const float2* __restrict__ s_tws, float2* __restrict__ scr,
+                                          cplx (&z)[NF][FftGeom<N>::R1], float (&energy)[NF], int l,
+                                          bool last_ok0, bool last_ok1, bool want_energy, const StftParams& p) {
   using Geo = FftGeom<N>;
-  constexpr int NC = Geo::NC, G = Geo::G, R1 = Geo::R1, NSUB = Geo::NSUB;
-  constexpr int TS = TcTile<N>::kStride;
+  constexpr int G = Geo::G, R1 = Geo::R1, NSUB = Geo::NSUB;
   constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
-  const int partner = (G - l) % G;
   const bool odd_shift = (p.S & 1) != 0;  // kernel-uniform
   const cplx* wp = reinterpret_cast<const cplx*>(s_w) + l;
-  cplx z[NF][R1];
   cplx energy2[NF];
 #pragma unroll
   for (int f = 0; f < NF; ++f) energy2[f] = cmake(0.f, 0.f);
@@ -546,7 +547,17 @@ __device__ __forceinline__ void fft_frames(const float* const (&fx)[NF], const f
     }
     __syncwarp();
   }
-  // real-FFT split: lane l pairs its lower-half registers with the partner's upper half
+}
+
+// second part: real-FFT split (lane l pairs its lower-half registers with the partner's upper
+// half) and |X|^p -> pcol[f][bin * TS]
+template <int N, bool POWER, int NF>
+__device__ __forceinline__ void fft_back(cplx (&z)[NF][FftGeom<N>::R1], const float2* __restrict__ s_twp,
+                                         float* const (&pcol)[NF], int l) {
+  using Geo = FftGeom<N>;
+  constexpr int NC = Geo::NC, G = Geo::G, R1 = Geo::R1;
+  constexpr int TS = TcTile<N>::kStride;
+  const int partner = (G - l) % G;
 #pragma unroll
   for (int m = 0; m < R1 / 2; ++m) {
     const float2 w = s_twp[m * G + l];
@@ -578,6 +589,17 @@ __device__ __forceinline__ void fft_frames(const float* const (&fx)[NF], const f
       pcol[f][(NC / 2) * TS] = pk;
     }
   }
+}
+
+template <int N, bool POWER, int MODE, int NF>
+__device__ __forceinline__ void fft_frames(const float* const (&fx)[NF], const float* __restrict__ s_w,
+                                           const float2* __restrict__ s_tws, const float2* __restrict__ s_twp,
+                                           float2* __restrict__ scr, float* const (&pcol)[NF],
+                                           float (&energy)[NF], int l, bool last_ok0, bool last_ok1,
+                                           bool want_energy, const StftParams& p) {
+  cplx z[NF][FftGeom<N>::R1];
+  fft_front<N, MODE, NF>(fx, s_w, s_tws, scr, z, energy, l, last_ok0, last_ok1, want_energy, p);
+  fft_back<N, POWER, NF>(z, s_twp, pcol, l);
 }
 
 // shared-memory carve-up shared by host (size computation) and device
@@ -1074,6 +1096,584 @@ __global__ void __launch_bounds__(kThreads, (N <= 512 ? 2 : 1))
 }
 
 // ------------------------------------------------------------------------------------------
+// stft_tc2_kernel: the same tile pipeline with the phases cut differently (two frames per
+// sub-group, R1 <= 16).  The transform is split where it first touches the power-spectrum tile:
+//
+//   phase A : filter bank of the PREVIOUS tile (reads s_P), then window / energy / both DFT
+//             stages of THIS tile (reads s_x, private scratch; spectra stay in registers)
+//   barrier : s_x is free (the next TMA copy starts), every warp is done with the old s_P
+//   phase B : real-FFT split and |X|^p of this tile -> s_P
+//   barrier : s_P is complete
+//
+// In stft_tc_kernel the bank phase stands alone between two barriers: its ten unequal work items
+// leave warps idle (15 % of all warp time is spent at the barriers) and, being latency bound, it
+// keeps the FMA pipe idle while it lasts.  Here the bank items run side by side with other warps'
+// butterflies, and their imbalance is diluted in a phase three times as long.
+// ------------------------------------------------------------------------------------------
+template <int N, bool POWER, typename T, int MODE, int PROBE = 0>
+__global__ void __launch_bounds__(kThreads, 2) stft_tc2_kernel(const __grid_constant__ StftParams p) {
+  using Geo = FftGeom<N>;
+  using Lay = TcSmem<N>;
+  constexpr int G = Geo::G, R1 = Geo::R1;
+  static_assert(R1 <= 16 && TcTile<N>::kFrames == 2 * (kThreads / G), "two frames per sub-group cover one tile");
+  constexpr int FPR = kThreads / G;
+  constexpr int TS = TcTile<N>::kStride;
+  constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
+
+  extern __shared__ __align__(16) float smem[];
+  float* const s_x = smem + Lay::oX;
+  float* const s_w = smem + Lay::oW;
+  float2* const s_scr = reinterpret_cast<float2*>(smem + Lay::oScr);
+  float* const s_P = smem + Lay::oP;
+  uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + Lay::oBar);
+  int* const s_ctl = reinterpret_cast<int*>(smem + Lay::oCtl);
+  int4* const s_raw = reinterpret_cast<int4*>(smem + Lay::oRaw);
+  int* const s_wstart = reinterpret_cast<int*>(smem + Lay::oWstart);
+  int4* const s_items = reinterpret_cast<int4*>(smem + Lay::oItems);
+
+  const int tid = threadIdx.x;
+  const int sub = tid / G, l = tid % G;
+  const int n_tiles = (int)p.n_tiles, stride = gridDim.x;
+
+  // ---- one-time CTA set-up (as in stft_tc_kernel) ------------------------------------------
+  for (int i = tid; i < N; i += kThreads) s_w[i] = p.window[i];
+  for (int i = tid; i < p.tc_nitems; i += kThreads) s_items[i] = p.tc_items[i];
+  if (tid <= kThreads / 32) s_wstart[tid] = p.tc_wstart[tid];
+  for (int i = tid; i < Lay::kProws * TS; i += kThreads) s_P[i] = 0.f;
+  for (int i = tid; i < Lay::x_floats(p.span_max, p.L); i += kThreads) s_x[i] = 0.f;
+  float2* const s_tws = reinterpret_cast<float2*>(smem + Lay::oTws);
+  float2* const s_twp = reinterpret_cast<float2*>(smem + Lay::oTwp);
+  for (int i = tid; i < R1 * G; i += kThreads) s_tws[i] = p.tw_stage[(i % G) * R1 + i / G];
+  for (int i = tid; i < (R1 / 2) * G; i += kThreads) s_twp[i] = p.tw_split[(i % G) * (R1 / 2) + i / G];
+  int ti = blockIdx.x;
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (ti < n_tiles) {
+      const pds_tile first = p.tiles[ti];
+      tc_prepare<T>(p, first, s_ctl);
+      if (ti + stride < n_tiles) {
+        const int4* src = reinterpret_cast<const int4*>(p.tiles + ti + stride);
+        cp_async16(s_raw + 2, src);
+        cp_async16(s_raw + 3, src + 1);
+      }
+      cp_async_commit();
+    }
+  }
+  const bool last_ok0 = 2 * (G * (ROWS - 1) + l) < p.L;
+  const bool last_ok1 = 2 * (G * (ROWS - 1) + l) + 1 < p.L;
+  float2* const scr = s_scr + sub * Geo::SCR_FLOAT2;
+  const bool want_energy = p.include_energy != 0;
+  __syncthreads();
+  if (ti >= n_tiles) return;
+
+  if (tid == 0) tc_issue<T>(p, s_ctl, s_x, s_bar);
+  if (s_ctl[kCtlFlags] & kFlagHandStaged) {
+    stage_samples_slow<T, kThreads>(s_x, p, tc_tile_of(s_ctl), s_ctl[kCtlSpan], s_ctl[kCtlA0], s_ctl[kCtlA1]);
+    __syncthreads();
+  }
+
+  float* prev_out = nullptr;  // the tile whose power spectra sit in s_P
+  int prev_frames = 0;
+  for (int it = 0; ti < n_tiles; ti += stride, ++it) {
+    const int* __restrict__ c = s_ctl + (it & 1) * 16;
+    const int* __restrict__ cn = s_ctl + ((it + 1) & 1) * 16;
+    const int4 c0 = *reinterpret_cast<const int4*>(c);
+    const int nframes = c0.x;
+    float* __restrict__ out_tile = p.out + (((long long)c0.w << 32) | (unsigned)c0.z);
+    const bool has_next = ti + stride < n_tiles;
+    if (tid == 0 && has_next) {
+      cp_async_wait_all();
+      const int4* raw = s_raw + 2 * ((it + 1) & 1);
+      const int4 r0 = raw[0], r1 = raw[1];
+      pds_tile nt;
+      nt.sig_off = ((long long)r0.y << 32) | (unsigned)r0.x;
+      nt.sig_len = r0.z;
+      nt.start = r0.w;
+      nt.nframes = r1.x;
+      nt.utt = r1.y;
+      nt.out_row = ((long long)r1.w << 32) | (unsigned)r1.z;
+      tc_prepare<T>(p, nt, s_ctl + ((it + 1) & 1) * 16);
+      if (ti + 2 * stride < n_tiles) {
+        const int4* src = reinterpret_cast<const int4*>(p.tiles + ti + 2 * stride);
+        cp_async16(s_raw + 2 * (it & 1), src);
+        cp_async16(s_raw + 2 * (it & 1) + 1, src + 1);
+      }
+      cp_async_commit();
+    }
+
+    // ---- phase A: bank of the previous tile, then the front of this tile's transform ------
+    if (it > 0 && PROBE != 1) bank_tc<TS>(tid >> 5, tid & 31, s_P, s_items, s_wstart, p.tc_frags, p, prev_out, prev_frames);
+    mbar_wait(s_bar, it & 1);
+    // sub-groups past the end recompute the last frame (identical writes): full-warp shuffles
+    const int ta = min(sub, nframes - 1), tb = min(sub + FPR, nframes - 1);
+    cplx z[2][R1];
+    if (PROBE != 2) {
+      const float* const fx[2] = {s_x + ta * p.S, s_x + tb * p.S};
+      float en[2] = {0.f, 0.f};
+      fft_front<N, MODE, 2>(fx, s_w, s_tws, scr, z, en, l, last_ok0, last_ok1, want_energy, p);
+      if (want_energy && l == 0) {  // energy column (compute.py:392-398)
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          float v = en[f] * p.inv_L;
+          if (!POWER) v = sqrtf(v);
+          if (p.use_log) v = fast_log(fmaxf(v, p.log_floor));
+          __stcs(out_tile + (f ? tb : ta) * p.C, v);
+        }
+      }
+    }
+    __syncthreads();  // s_x is free again, nobody reads the previous s_P any more, next control block visible
+
+    if (has_next && tid == 0) tc_issue<T>(p, cn, s_x, s_bar);
+
+    // ---- phase B: split + |X|^p -> s_P ------------------------------------------------------
+    if (PROBE != 2) {
+      float* const pc[2] = {s_P + ta, s_P + tb};
+      fft_back<N, POWER, 2>(z, s_twp, pc, l);
+    }
+    if (has_next && (cn[kCtlFlags] & kFlagHandStaged))
+      stage_samples_slow<T, kThreads>(s_x, p, tc_tile_of(cn), cn[kCtlSpan], cn[kCtlA0], cn[kCtlA1]);
+    prev_out = out_tile;
+    prev_frames = nframes;
+    __syncthreads();  // s_P is complete, hand-staged samples are visible
+  }
+  if (PROBE != 1) bank_tc<TS>(tid >> 5, tid & 31, s_P, s_items, s_wstart, p.tc_frags, p, prev_out, prev_frames);
+}
+
+// ------------------------------------------------------------------------------------------
+// stft_w_kernel: warp-specialised pipeline, one 512-thread CTA per SM, no CTA-wide barriers.
+//
+//   warps 0..11  transform : three groups of four warps.  A group owns a stream of 16-frame tiles
+//                            (one m16 MMA tile); a warp transforms four of the frames (two per
+//                            half-warp, as in stft_tc2_kernel) and writes their power spectra to
+//                            the group's tile P[g][stage] (two stages).
+//   warps 12..14 bank      : warp 12 + g applies the filter bank to the tiles of group g on the
+//                            tensor cores and stores the features (block-major: the A fragments
+//                            of a 16-bin block are loaded and split into tf32 hi / lo once and
+//                            used for every filter group whose band covers the block).
+//   warp  15     producer  : lane g fetches the tile descriptors of group g, prepares the control
+//                            blocks and issues the TMA bulk copies into the group's two sample
+//                            stages.
+//
+// Hand-over is by mbarriers only (x_full / x_empty per sample stage, p_full / p_empty per spectrum
+// stage).  The transform is bound by the FMA pipe and the bank by latency; in the phased kernels
+// the two alternate (4.7 ms + 3.1 ms when timed alone, 7.1 ms together), here the bank's
+// instructions fill the issue slots the butterflies leave free.  Shared memory: the exchange
+// scratch of a half-warp aliases the two P columns it is about to write (they are dead between
+// the bank warp's p_empty and this warp's own split), which is what makes room for double-buffered
+// spectra, double-buffered samples and the weight fragments (220 KB).
+//
+// Used for float32 input without fused pre-processing, dft_size 512 geometry (G = R1 = 16), at
+// most 64 filters whose weight fragments fit the budget; everything else runs stft_tc2_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int kWThreads = 512;
+constexpr int kWGroups = 3;          // groups of four transform warps
+constexpr int kWTile = 16;           // frames per tile
+constexpr int kWStride = 18;         // floats per row of a spectrum tile (conflict free, see TcTile)
+constexpr int kWRows = 272;          // rows per spectrum tile: 257 bins padded to 17 blocks of 16
+constexpr int kWBlocks = kWRows / 16;
+constexpr int kWRing = 8;            // control blocks per group
+constexpr int kWMaxNT = 8;           // filter groups of eight (F <= 64)
+
+struct WLayout {  // offsets in floats; every region 16-byte aligned
+  static constexpr int oW = 0;                                  // window [512]
+  static constexpr int oTws = oW + 512;                         // stage twiddles [16][16] float2
+  static constexpr int oTwp = oTws + 512;                       // split twiddles [8][16] float2
+  static constexpr int oBar = oTwp + 256;                       // 24 mbarriers
+  static constexpr int oCtl = oBar + 64;                        // control blocks [3][8][16] ints
+  static constexpr int oTab = oCtl + kWGroups * kWRing * 16;    // block masks [32] + per-filter-group offsets [8]
+  static constexpr int oP = oTab + 48;                          // spectra [3][2][272][18]
+  static constexpr int oX = oP + kWGroups * 2 * kWRows * kWStride;  // samples [3][2][xstride]
+  static_assert(oBar % 4 == 0 && oCtl % 4 == 0 && oTab % 4 == 0 && oP % 4 == 0 && oX % 4 == 0, "16-byte regions");
+  static __host__ __device__ constexpr int xstride(int span_max, int L) { return (span_max + (512 - L) + 32 + 3) & ~3; }
+  static __host__ __device__ constexpr int o_frag(int span_max, int L) { return oX + kWGroups * 2 * xstride(span_max, L); }
+  static __host__ __device__ constexpr size_t bytes(int span_max, int L, int frag_float4) {
+    return sizeof(float) * ((size_t)o_frag(span_max, L) + 4 * (size_t)frag_float4);
+  }
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// bank warp: features of one 16-frame tile from its power spectra (compute.py:416-460)
+template <int NT>
+__device__ __forceinline__ void bank_w(int lane, const float* __restrict__ P, const int* __restrict__ s_mask,
+                                       const int* __restrict__ s_adj, const float4* __restrict__ s_frag,
+                                       const StftParams& p, float* __restrict__ out_tile, int nframes) {
+  constexpr int TS = kWStride;
+  constexpr int NS = NT <= 5 ? 2 : 1;  // separate accumulators per k-step parity while the registers last
+  const int g = lane >> 2, t = lane & 3;
+  float acc[NT][NS][2][4];  // [filter group][k-step parity][main | correction][fragment]
+#pragma unroll
+  for (int n = 0; n < NT; ++n)
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2)
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[n][s2][q][i] = 0.f;
+  const float* __restrict__ pa = P + 4 * t * TS + g;
+  const float4* __restrict__ frl = s_frag + lane;
+  int adj[NT];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) adj[n] = s_adj[n];
+  float a[2][4];
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2) {
+    a[s2][0] = pa[(2 * s2) * TS], a[s2][1] = pa[(2 * s2) * TS + 8];
+    a[s2][2] = pa[(2 * s2 + 1) * TS], a[s2][3] = pa[(2 * s2 + 1) * TS + 8];
+  }
+#pragma unroll
+  for (int b = 0; b < kWBlocks; ++b) {
+    const int mask = s_mask[b];
+    uint32_t hi[2][4], lo[2][4];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        hi[s2][i] = __float_as_uint(a[s2][i]) & 0xffffe000u;
+        lo[s2][i] = __float_as_uint(a[s2][i] - __uint_as_float(hi[s2][i]));
+      }
+    if (b + 1 < kWBlocks) {  // the next block's spectra are in flight while this block's MMAs run
+      const float* __restrict__ pn = pa + (b + 1) * 16 * TS;
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        a[s2][0] = pn[(2 * s2) * TS], a[s2][1] = pn[(2 * s2) * TS + 8];
+        a[s2][2] = pn[(2 * s2 + 1) * TS], a[s2][3] = pn[(2 * s2 + 1) * TS + 8];
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      if (mask & (1 << n)) {
+        const float4* __restrict__ fr = frl + (adj[n] + b * 64);
+        const float4 f0 = fr[0], f1 = fr[32];
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const float4 f = s2 ? f1 : f0;
+          const uint32_t whi0 = __float_as_uint(f.x), whi1 = __float_as_uint(f.y);
+          const uint32_t wlo0 = __float_as_uint(f.z), wlo1 = __float_as_uint(f.w);
+          float(&am)[4] = acc[n][NS == 2 ? s2 : 0][0];
+          float(&ac)[4] = acc[n][NS == 2 ? s2 : 0][1];
+          mma_tf32(am, hi[s2][0], hi[s2][1], hi[s2][2], hi[s2][3], whi0, whi1);
+          mma_tf32(ac, lo[s2][0], lo[s2][1], lo[s2][2], lo[s2][3], whi0, whi1);
+          mma_tf32(ac, hi[s2][0], hi[s2][1], hi[s2][2], hi[s2][3], wlo0, wlo1);
+        }
+      }
+    }
+  }
+  const bool use_log = p.use_log != 0;
+  const float log_floor = p.log_floor;
+  const int C = p.C;
+  float* __restrict__ r0 = out_tile + (g * C + p.include_energy + 2 * t);
+  float* __restrict__ r1 = r0 + 8 * C;
+  const bool row0 = g < nframes, row1 = g + 8 < nframes;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (NS == 2) v[i] = (acc[n][0][1][i] + acc[n][NS - 1][1][i]) + (acc[n][0][0][i] + acc[n][NS - 1][0][i]);
+      else v[i] = acc[n][0][1][i] + acc[n][0][0][i];
+      if (use_log) v[i] = fast_log(fmaxf(v[i], log_floor));
+    }
+    const bool c0 = 8 * n + 2 * t < p.F, c1 = 8 * n + 2 * t + 1 < p.F;
+    if (row0) {
+      if (c0) __stcs(r0 + 8 * n, v[0]);
+      if (c1) __stcs(r0 + 8 * n + 1, v[1]);
+    }
+    if (row1) {
+      if (c0) __stcs(r1 + 8 * n, v[2]);
+      if (c1) __stcs(r1 + 8 * n + 1, v[3]);
+    }
+  }
+}
+
+template <bool POWER, int MODE, int NT>
+__global__ void __launch_bounds__(kWThreads, 1) stft_w_kernel(const __grid_constant__ StftParams p) {
+  constexpr int N = 512;
+  using Geo = FftGeom<N>;
+  using Lay = WLayout;
+  constexpr int NC = Geo::NC, G = Geo::G, R1 = Geo::R1;
+  static_assert(G == 16 && R1 == 16, "one frame pair per half-warp");
+  constexpr int TS = kWStride;
+  constexpr int ROWS = MODE == kRows13 ? (R1 * 13) / 16 : R1;
+
+  extern __shared__ __align__(16) float smem[];
+  float* const s_w = smem + Lay::oW;
+  float2* const s_tws = reinterpret_cast<float2*>(smem + Lay::oTws);
+  float2* const s_twp = reinterpret_cast<float2*>(smem + Lay::oTwp);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + Lay::oBar);
+  uint64_t* const x_full = bars;        // [3][2]
+  uint64_t* const x_empty = bars + 6;   // [3][2]
+  uint64_t* const p_full = bars + 12;   // [3][2]
+  uint64_t* const p_empty = bars + 18;  // [3][2]
+  int* const s_ctl = reinterpret_cast<int*>(smem + Lay::oCtl);
+  int* const s_mask = reinterpret_cast<int*>(smem + Lay::oTab);
+  int* const s_adj = s_mask + 32;
+  float* const s_P = smem + Lay::oP;
+  float* const s_x = smem + Lay::oX;
+  const int xstride = Lay::xstride(p.span_max, p.L);
+  float4* const s_frag = reinterpret_cast<float4*>(smem + Lay::o_frag(p.span_max, p.L));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time CTA set-up -------------------------------------------------------------
+  for (int i = tid; i < N; i += kWThreads) s_w[i] = p.window[i];
+  for (int i = tid; i < R1 * G; i += kWThreads) s_tws[i] = p.tw_stage[(i % G) * R1 + i / G];
+  for (int i = tid; i < (R1 / 2) * G; i += kWThreads) s_twp[i] = p.tw_split[(i % G) * (R1 / 2) + i / G];
+  for (int i = tid; i < kWGroups * 2 * kWRows * TS; i += kWThreads) s_P[i] = 0.f;
+  for (int i = tid; i < kWGroups * 2 * xstride; i += kWThreads) s_x[i] = 0.f;  // slack must stay finite
+  for (int i = tid; i < p.w_frag4; i += kWThreads) s_frag[i] = p.tc_frags[i];
+  if (tid < 40) s_mask[tid] = 0;
+  __syncthreads();
+  if (tid < p.tc_nitems) {  // the bank items with m0 == 0 describe each filter group once
+    const int4 d = p.tc_items[tid];
+    if ((d.x >> 16) == 0) {
+      const int n = (d.x & 0xffff) >> 3;
+      s_adj[n] = d.w - d.y * 64;
+      for (int b = d.y; b < d.y + d.z; ++b) atomicOr(&s_mask[b], 1 << n);
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_empty[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int n_tiles = (int)p.n_tiles;
+  const int tile_step = kWGroups * gridDim.x;
+
+  if (warp < 4 * kWGroups) {
+    // =============================== transform warps ====================================
+    const int g = warp >> 2, wg = warp & 3;
+    const int h = lane >> 4, l = lane & 15;
+    const int col = 4 * wg + 2 * h;  // this half-warp's frames are col and col + 1 of the tile
+    const int first = blockIdx.x * kWGroups + g;
+    const int n_iter = first < n_tiles ? (n_tiles - first + tile_step - 1) / tile_step : 0;
+    const bool last_ok0 = 2 * (G * (ROWS - 1) + l) < p.L;
+    const bool last_ok1 = 2 * (G * (ROWS - 1) + l) + 1 < p.L;
+    const bool want_energy = p.include_energy != 0;
+    const cplx* wp = reinterpret_cast<const cplx*>(s_w) + l;
+    const cplx last_mask = cmake(last_ok0 ? 1.f : 0.f, last_ok1 ? 1.f : 0.f);
+    const int partner = (G - l) % G;
+    for (int j = 0; j < n_iter; ++j) {
+      const int st = g * 2 + (j & 1);
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&x_full[st], ph);
+      const int* __restrict__ c = s_ctl + (g * kWRing + (j & (kWRing - 1))) * 16;
+      const int4 c0 = *reinterpret_cast<const int4*>(c);
+      const int nframes = c0.x;
+      float* __restrict__ out_tile = p.out + (((long long)c0.w << 32) | (unsigned)c0.z);
+      float* const sx = s_x + st * xstride;
+      if (c0.y & kFlagHandStaged) {  // utterance edges: the four warps fill in the reflected samples
+        stage_samples_slow<float, 128>(sx, p, tc_tile_of(c), c[kCtlSpan], c[kCtlA0], c[kCtlA1], tid & 127);
+        named_bar_sync(1 + g, 128);
+      }
+      // Frames col and col + 1 are transformed even when the tile is shorter (they then read stale,
+      // finite samples); their energies are not stored and the bank masks their rows.
+      const float* const fx[2] = {sx + col * p.S, sx + (col + 1) * p.S};
+      cplx z[2][R1];
+      if (p.w_probe == 2) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x_empty[st]);
+        mbar_wait(&p_empty[st], ph ^ 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[st]);
+        continue;
+      }
+      // ---- window, energy (compute.py:392-398), first DFT stage, twiddle -----------------
+      {
+        cplx energy2[2] = {cmake(0.f, 0.f), cmake(0.f, 0.f)};
+        // S == 2 G SH: row r of frame col + 1 is row r + SH of frame col -- one load serves both
+        constexpr int SH = 5;
+        if (MODE != kRowsAny && p.S == 2 * G * SH) {
+          cplx x[ROWS + SH];
+#pragma unroll
+          for (int r = 0; r < ROWS + SH; ++r) x[r] = reinterpret_cast<const cplx*>(fx[0])[l + G * r];
+#pragma unroll
+          for (int r = 0; r < R1; ++r) {
+            if (r < ROWS) {
+              const cplx w = wp[G * r];
+#pragma unroll
+              for (int f = 0; f < 2; ++f) {
+                cplx xv = x[r + f * SH];
+                z[f][r] = cmul2(xv, w);
+                if (r == ROWS - 1) xv = cmul2(xv, last_mask);
+                energy2[f] = cfma2(xv, xv, energy2[f]);
+              }
+            } else {
+              z[0][r] = z[1][r] = cmake(0.f, 0.f);
+            }
+          }
+        } else {
+          const bool odd_shift = (p.S & 1) != 0;
+#pragma unroll
+          for (int r = 0; r < R1; ++r) {
+            if (r < ROWS) {
+              const cplx w = wp[G * r];
+#pragma unroll
+              for (int f = 0; f < 2; ++f) {
+                cplx x;
+                if (MODE == kRowsAny && odd_shift) {
+                  const float* q = fx[f] + 2 * (l + G * r);
+                  x = cmake(q[0], q[1]);
+                } else {
+                  x = reinterpret_cast<const cplx*>(fx[f])[l + G * r];
+                }
+                z[f][r] = cmul2(x, w);
+                if (MODE == kRowsAny) {
+                  x = cmul2(x, cmake(2 * (G * r + l) < p.L ? 1.f : 0.f, 2 * (G * r + l) + 1 < p.L ? 1.f : 0.f));
+                } else if (r == ROWS - 1) {
+                  x = cmul2(x, last_mask);
+                }
+                energy2[f] = cfma2(x, x, energy2[f]);
+              }
+            } else {
+#pragma unroll
+              for (int f = 0; f < 2; ++f) z[f][r] = cmake(0.f, 0.f);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x_empty[st]);  // the samples are in registers
+        if (want_energy) {
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            float e = cre(energy2[f]) + cim(energy2[f]);
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off, G);
+            if (l == 0 && col + f < nframes) {
+              float v = e * p.inv_L;
+              if (!POWER) v = sqrtf(v);
+              if (p.use_log) v = fast_log(fmaxf(v, p.log_floor));
+              __stcs(out_tile + (col + f) * p.C, v);
+            }
+          }
+        }
+        constexpr unsigned ZROWS = ROWS >= R1 ? 0u : (zmask_full<R1>() & ~((1u << ROWS) - 1u));
+#pragma unroll
+        for (int f = 0; f < 2; ++f) Dft<R1, ZROWS>::run(z[f]);
+#pragma unroll
+        for (int k1 = 1; k1 < R1; ++k1) {
+          const float2 tw = s_tws[k1 * G + l];
+#pragma unroll
+          for (int f = 0; f < 2; ++f) z[f][k1] = cmul(z[f][k1], tw);
+        }
+      }
+      // ---- exchange through this half-warp's two columns of P[g][stage], second DFT stage ----
+      mbar_wait(&p_empty[st], ph ^ 1);  // the bank warp is done with the tile two iterations back
+      float* const Pst = s_P + st * (kWRows * TS);
+      {
+        cplx* const cs = reinterpret_cast<cplx*>(Pst + col);  // slot j = row j, columns col / col + 1
+        constexpr int SLOT = TS / 2;                          // cplx units per row
+        // the frames take turns in the one scratch; the second frame's stores and loads are issued
+        // before the first frame's butterflies so that their latency hides behind the arithmetic
+        cplx v0[G], v1[G];
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) cs[(17 * l + k1) * SLOT] = z[0][k1];
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < G; ++n2) v0[n2] = cs[(17 * n2 + l) * SLOT];
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) cs[(17 * l + k1) * SLOT] = z[1][k1];
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < G; ++n2) v1[n2] = cs[(17 * n2 + l) * SLOT];
+        Dft<G>::run(v0);
+        Dft<G>::run(v1);
+#pragma unroll
+        for (int k2 = 0; k2 < G; ++k2) z[0][k2] = v0[k2], z[1][k2] = v1[k2];
+        __syncwarp();
+        if (l < kWRows - 257) cs[(257 + l) * SLOT] = cmake(0.f, 0.f);  // the padding rows are zeros again
+      }
+      // ---- real-FFT split, |X|^p of both frames -> P[bin][col .. col + 1] --------------------
+      {
+        float2* const pc = reinterpret_cast<float2*>(Pst + col);
+        constexpr int SLOT = TS / 2;
+#pragma unroll
+        for (int m = 0; m < R1 / 2; ++m) {
+          const float2 w = s_twp[m * G + l];
+          float pk[2], pq[2];
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            cplx b;
+            b.v = __shfl_sync(0xffffffffu, z[f][R1 - 1 - m].v, partner, G);
+            if (l == 0) b = z[f][(R1 - m) % R1];
+            cplx xk, xq;
+            split_pair(z[f][m], b, w, xk, xq);
+            pk[f] = cnorm(xk), pq[f] = cnorm(xq);
+            if (!POWER) {
+              pk[f] = sqrtf(pk[f]);
+              pq[f] = sqrtf(pq[f]);
+            }
+          }
+          const int k = l + G * m;
+          pc[k * SLOT] = make_float2(pk[0], pk[1]);
+          pc[(NC - k) * SLOT] = make_float2(pq[0], pq[1]);
+        }
+        if (l == 0) {  // bin NC/2 pairs with itself; its twiddle is -i
+          float pk[2];
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            const cplx a = z[f][R1 / 2];
+            cplx xk, xq;
+            split_pair(a, a, make_float2(0.f, -1.f), xk, xq);
+            pk[f] = cnorm(xk);
+            if (!POWER) pk[f] = sqrtf(pk[f]);
+          }
+          pc[(NC / 2) * SLOT] = make_float2(pk[0], pk[1]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[st]);
+    }
+  } else if (warp < 4 * kWGroups + kWGroups) {
+    // =============================== bank warps =========================================
+    const int g = warp - 4 * kWGroups;
+    const int first = blockIdx.x * kWGroups + g;
+    const int n_iter = first < n_tiles ? (n_tiles - first + tile_step - 1) / tile_step : 0;
+    for (int j = 0; j < n_iter; ++j) {
+      const int st = g * 2 + (j & 1);
+      mbar_wait(&p_full[st], (j >> 1) & 1);
+      const int* __restrict__ c = s_ctl + (g * kWRing + (j & (kWRing - 1))) * 16;
+      const int4 c0 = *reinterpret_cast<const int4*>(c);
+      float* __restrict__ out_tile = p.out + (((long long)c0.w << 32) | (unsigned)c0.z);
+      if (p.w_probe != 1) bank_w<NT>(lane, s_P + st * (kWRows * TS), s_mask, s_adj, s_frag, p, out_tile, c0.x);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_empty[st]);
+    }
+  } else if (lane < kWGroups) {
+    // =============================== producer lanes =====================================
+    const int g = lane;
+    const int first = blockIdx.x * kWGroups + g;
+    const int n_iter = first < n_tiles ? (n_tiles - first + tile_step - 1) / tile_step : 0;
+    for (int j = 0; j < n_iter; ++j) {
+      const int st = g * 2 + (j & 1);
+      const int4* src = reinterpret_cast<const int4*>(p.tiles + first + (long long)j * tile_step);
+      const int4 r0 = __ldg(src), r1 = __ldg(src + 1);
+      pds_tile nt;
+      nt.sig_off = ((long long)r0.y << 32) | (unsigned)r0.x;
+      nt.sig_len = r0.z;
+      nt.start = r0.w;
+      nt.nframes = r1.x;
+      nt.utt = r1.y;
+      nt.out_row = ((long long)r1.w << 32) | (unsigned)r1.z;
+      int* c = s_ctl + (g * kWRing + (j & (kWRing - 1))) * 16;
+      tc_prepare<float>(p, nt, c);
+      if (j >= 2) mbar_wait(&x_empty[st], ((j - 2) >> 1) & 1);  // all four warps have consumed the stage
+      tc_issue<float>(p, c, s_x + st * xstride, &x_full[st]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // software-pipelined variant (one CTA per SM, no CTA-wide barriers in steady state)
 //
 //   warps 0..15  compute : every iteration  A) fft of this warp's two frames of tile i
@@ -1434,6 +2034,14 @@ struct pds_stft_plan {
   size_t ws_smem_bytes = 0;
   bool fused = false;  // scalar-bank kernel compiled for this size (N = 512 only: A/B runs, > 96 work items)
   bool tc = false;  // tensor-core bank kernel available (the default fast path)
+  // PDS_STFT_KERNEL, read once when the plan is made: unset = stft_w_kernel where it applies
+  // (else stft_tc2_kernel), '2' = stft_tc2_kernel, '1' = stft_tc_kernel, 's' = scalar-bank
+  // kernel, 'w' = the round-1 software-pipelined kernel
+  int variant = 5;
+  bool want_ws = false, want_scalar = false;
+  bool w = false;  // stft_w_kernel usable (float32 input; 16-frame tiles)
+  size_t w_smem_bytes = 0;
+  int w_nt = 0;
   size_t tc_smem_bytes = 0;
   int tc_grid_limit = 0;
   bool power = false;
@@ -1480,32 +2088,66 @@ constexpr int tc_frames() {
 }
 
 template <int N, int MODE>
-KernelFn pick_tc_mode(bool power, int dtype) {
+KernelFn pick_tc2_mode(bool power, int dtype) {
+  if constexpr (FftGeom<N>::R1 <= 16 && TcTile<N>::kFrames == 2 * (kThreads / FftGeom<N>::G)) {
+    if (power) return dtype == PDS_I16 ? stft_tc2_kernel<N, true, short, MODE> : stft_tc2_kernel<N, true, float, MODE>;
+    return dtype == PDS_I16 ? stft_tc2_kernel<N, false, short, MODE> : stft_tc2_kernel<N, false, float, MODE>;
+  } else {
+    return nullptr;
+  }
+}
+
+template <int N, int MODE>
+KernelFn pick_tc_mode(bool power, int dtype, int variant) {
+  if (variant == 2) {
+    KernelFn fn = pick_tc2_mode<N, MODE>(power, dtype);
+    if (fn) return fn;
+  }
+#ifdef PDS_DEV_N512_ONLY
+  if constexpr (N == 512 && MODE == kRows13) {
+    if (variant == 3) return stft_tc2_kernel<512, true, float, kRows13, 1>;  // probe: no bank phase
+    if (variant == 4) return stft_tc2_kernel<512, true, float, kRows13, 2>;  // probe: no fft phase
+  }
+#endif
   constexpr int NF = tc_frames<N>();
   if (power) return dtype == PDS_I16 ? stft_tc_kernel<N, true, short, MODE, NF> : stft_tc_kernel<N, true, float, MODE, NF>;
   return dtype == PDS_I16 ? stft_tc_kernel<N, false, short, MODE, NF> : stft_tc_kernel<N, false, float, MODE, NF>;
 }
 
 template <int N>
-KernelFn pick_tc_n(bool power, int dtype, int mode) {
+KernelFn pick_tc_n(bool power, int dtype, int mode, int variant) {
   switch (mode) {
-    case kRows13: return pick_tc_mode<N, kRows13>(power, dtype);
-    case kRows16: return pick_tc_mode<N, kRows16>(power, dtype);
-    default: return pick_tc_mode<N, kRowsAny>(power, dtype);
+    case kRows13: return pick_tc_mode<N, kRows13>(power, dtype, variant);
+    case kRows16: return pick_tc_mode<N, kRows16>(power, dtype, variant);
+    default: return pick_tc_mode<N, kRowsAny>(power, dtype, variant);
   }
 }
 
 KernelFn pick_tc(const pds_stft_plan* plan, int dtype) {
   switch (plan->N) {
 #ifndef PDS_DEV_N512_ONLY
-    case 256: return pick_tc_n<256>(plan->power, dtype, plan->row_mode);
+    case 256: return pick_tc_n<256>(plan->power, dtype, plan->row_mode, plan->variant);
 #endif
-    case 512: return pick_tc_n<512>(plan->power, dtype, plan->row_mode);
+    case 512: return pick_tc_n<512>(plan->power, dtype, plan->row_mode, plan->variant);
 #ifndef PDS_DEV_N512_ONLY
-    case 1024: return pick_tc_n<1024>(plan->power, dtype, plan->row_mode);
-    case 2048: return pick_tc_n<2048>(plan->power, dtype, plan->row_mode);
+    case 1024: return pick_tc_n<1024>(plan->power, dtype, plan->row_mode, plan->variant);
+    case 2048: return pick_tc_n<2048>(plan->power, dtype, plan->row_mode, plan->variant);
 #endif
     default: return nullptr;
+  }
+}
+
+template <int MODE>
+KernelFn pick_w_mode(bool power, int nt) {
+  if (power) return nt <= 5 ? stft_w_kernel<true, MODE, 5> : stft_w_kernel<true, MODE, 8>;
+  return nt <= 5 ? stft_w_kernel<false, MODE, 5> : stft_w_kernel<false, MODE, 8>;
+}
+
+KernelFn pick_w(const pds_stft_plan* plan) {
+  switch (plan->row_mode) {
+    case kRows13: return pick_w_mode<kRows13>(plan->power, plan->w_nt);
+    case kRows16: return pick_w_mode<kRows16>(plan->power, plan->w_nt);
+    default: return pick_w_mode<kRowsAny>(plan->power, plan->w_nt);
   }
 }
 
@@ -1567,7 +2209,8 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     set_error("no usable CUDA device %d (found %d); this library has no CPU fallback", device, ndev);
     return PDS_ERR_CUDA;
   }
-  PDS_CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  PDS_CUDA_CHECK(guard.status());
 
   pds_stft_plan* plan = new (std::nothrow) pds_stft_plan();
   if (!plan) return PDS_ERR_NOMEM;
@@ -1576,6 +2219,14 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   plan->C = F + (d->include_energy ? 1 : 0);
   plan->pad_left = d->pad_left;
   plan->power = d->use_power != 0;
+  if (const char* force = getenv("PDS_STFT_KERNEL")) {
+    plan->want_ws = force[0] == 'w';
+    plan->want_scalar = force[0] == 's';
+    if (force[0] == '1' || force[0] == 'w' || force[0] == 's') plan->variant = 1;
+    if (force[0] == '2') plan->variant = 2;
+    if (force[0] == 'x') plan->variant = 3;
+    if (force[0] == 'y') plan->variant = 4;
+  }
   cudaDeviceProp prop;
   cudaError_t err = cudaGetDeviceProperties(&prop, device);
   if (err != cudaSuccess) {
@@ -1729,6 +2380,18 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       plan->tc = tc_bytes <= smem_cap && F < 65536 && tc_p_rows <= tc_rows_max && tc_nitems <= tc_items_max;
       plan->tc_smem_bytes = tc_bytes;
     }
+    // warp-specialised kernel: dft_size 512, no fused pre-processing, <= 64 filters, everything in
+    // shared memory (16-frame tiles)
+    if (plan->tc && plan->variant == 5 && N == 512 && d->preemph == 0.f && d->dither == 0.f && F <= 8 * kWMaxNT) {
+      const int w_span = (kWTile - 1) * S + L;
+      const size_t w_bytes = WLayout::bytes(w_span, L, (int)(tc_frags.size() / 4));
+      if (w_bytes <= smem_cap) {
+        plan->w = true;
+        plan->w_smem_bytes = w_bytes;
+        plan->w_nt = (F + 7) / 8;
+        p.span_max = w_span;
+      }
+    }
     if (!plan->fused && !plan->tc) plan->fast = false;  // huge frame shift / dft_size 2048: direct kernel
     if (plan->fast && plan->fused && d->preemph == 0.f && d->dither == 0.f) {
       const WsLayout ws = ws_layout(N, G, R1, p.span_max, p_rows, npairs, plan->C, pair_total);
@@ -1744,7 +2407,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       return PDS_ERR_UNSUPPORTED;
     }
   }
-  plan->tile_frames = plan->fast ? (N > 1024 ? 16 : kTileFrames) : kDirectTileFrames;
+  plan->tile_frames = plan->fast ? (N > 1024 || plan->w ? 16 : kTileFrames) : kDirectTileFrames;
 
   // ---- build the constant tables on the host (double precision trig) --------------------
   std::vector<float> wt(std::max(wtotal, 4), 0.f);
@@ -1827,6 +2490,8 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   p.tc_wstart = reinterpret_cast<const int*>(base + o_tcw);
   p.tc_frags = reinterpret_cast<const float4*>(base + o_tcf);
   p.tc_nitems = tc_nitems;
+  p.w_frag4 = (int)(tc_frags.size() / 4);
+  p.w_probe = getenv("PDS_W_PROBE") ? atoi(getenv("PDS_W_PROBE")) : 0;
   p.tc_p_rows = tc_p_rows;
   p.p_rows = p_rows;
   p.weights = reinterpret_cast<const float*>(base + o_wt);
@@ -1862,6 +2527,15 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       }
     }
   }
+  if (plan->w) {
+    err = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_w(plan)),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->w_smem_bytes);
+    if (err != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", plan->w_smem_bytes, cudaGetErrorString(err));
+      pds_stft_plan_destroy(plan);
+      return PDS_ERR_CUDA;
+    }
+  }
   if (plan->ws) {
     err = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_ws<512>(plan->power, plan->row_mode)),
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->ws_smem_bytes);
@@ -1888,7 +2562,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
 
 extern "C" void pds_stft_plan_destroy(pds_stft_plan* plan) {
   if (!plan) return;
-  cudaSetDevice(plan->device);
+  DeviceGuard guard(plan->device);
   if (plan->d_blob) cudaFree(plan->d_blob);
   if (plan->d_sig) cudaFree(plan->d_sig);
   if (plan->d_tiles) cudaFree(plan->d_tiles);
@@ -1981,9 +2655,7 @@ extern "C" int pds_stft_run(pds_stft_plan* plan, const void* d_signal, int sig_d
   p.seed = seed;
   // PDS_STFT_KERNEL=ws opts in to the warp-specialised kernel (A/B runs, tests).  It is not the
   // default yet: its three bank warps are the bottleneck (profiles/), the phased kernel is faster.
-  const char* force = getenv("PDS_STFT_KERNEL");
-  const bool want_ws = force && force[0] == 'w';
-  if (plan->ws && sig_dtype == PDS_F32 && want_ws) {
+  if (plan->ws && sig_dtype == PDS_F32 && plan->want_ws) {
     const int grid = (int)std::min<int64_t>(n_tiles, plan->num_sms);
     pick_ws<512>(plan->power, plan->row_mode)<<<grid, kWsThreads, plan->ws_smem_bytes,
                                                 static_cast<cudaStream_t>(stream)>>>(p);
@@ -1991,8 +2663,15 @@ extern "C" int pds_stft_run(pds_stft_plan* plan, const void* d_signal, int sig_d
     return PDS_OK;
   }
   // PDS_STFT_KERNEL=scalar falls back to the CUDA-core bank kernel (A/B runs, tests)
-  const bool want_scalar = force && force[0] == 's';
-  if (plan->tc && !(want_scalar && plan->fused)) {
+  if (plan->w && sig_dtype == PDS_F32) {
+    PDS_REQUIRE((reinterpret_cast<uintptr_t>(d_tiles) & 15u) == 0, "d_tiles must be 16-byte aligned");
+    PDS_REQUIRE(n_tiles < ((int64_t)1 << 30), "at most 2^30 tiles per launch (got %lld)", (long long)n_tiles);
+    const int grid = (int)std::min<int64_t>((n_tiles + kWGroups - 1) / kWGroups, plan->num_sms);
+    pick_w(plan)<<<grid, kWThreads, plan->w_smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+    PDS_CUDA_CHECK(cudaGetLastError());
+    return PDS_OK;
+  }
+  if (plan->tc && !(plan->want_scalar && plan->fused)) {
     PDS_REQUIRE((reinterpret_cast<uintptr_t>(d_tiles) & 15u) == 0, "d_tiles must be 16-byte aligned");
     PDS_REQUIRE(n_tiles < ((int64_t)1 << 30), "at most 2^30 tiles per launch (got %lld)", (long long)n_tiles);
     const int grid = (int)std::min<int64_t>(n_tiles, plan->tc_grid_limit);
@@ -2039,7 +2718,8 @@ extern "C" int pds_stft_compute_host(pds_stft_plan* plan, const void* h_signal, 
               (long long)out_capacity_rows, (long long)rows);
   if (rows == 0) return PDS_OK;
   PDS_REQUIRE(h_signal && h_out, "null buffer");
-  PDS_CUDA_CHECK(cudaSetDevice(plan->device));
+  DeviceGuard guard(plan->device);
+  PDS_CUDA_CHECK(guard.status());
   std::vector<pds_tile> tiles((size_t)n_tiles);
   rc = pds_stft_fill_tiles(plan, n_utts, sig_off, sig_len, frame_off, tiles.data());
   if (rc != PDS_OK) return rc;

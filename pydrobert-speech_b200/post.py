@@ -53,22 +53,29 @@ class Standardize(PostProcessor):
     aliases = {"standardize", "normalize", "unit", "cmvn"}
 
     def __init__(self, rfilename: Optional[str] = None, norm_var: bool = True, **kwargs):
-        self._stats = None
+        # The statistics live on the GPU while they are being accumulated / reduced / applied
+        # (`_d_stats`, float64 (2, C+1)); `_h_stats` is the host copy, refreshed on demand.  Exactly
+        # one of the two is authoritative at any time (`_host_fresh`).
+        self._h_stats = None
+        self._d_stats = None
+        self._d_flag = None      # int32 device flag: a ~0 variance was replaced by 1
+        self._host_fresh = True
+        self._rows_seen = 0      # rows accumulated through this object (host-side bookkeeping, no sync)
         self._norm_var = bool(norm_var)
         if rfilename is not None:
             if "dtype" in kwargs:
-                self._stats = read_signal(rfilename, **kwargs)
+                self._h_stats = read_signal(rfilename, **kwargs)
             else:
                 for dtype in (np.float64, np.float32, "dm", "fm"):
                     try:
-                        self._stats = read_signal(rfilename, dtype=dtype, **kwargs)
+                        self._h_stats = read_signal(rfilename, dtype=dtype, **kwargs)
                         break
                     except (IOError, ValueError, ImportError, TypeError):
                         pass
-                if self._stats is None:
+                if self._h_stats is None:
                     raise IOError("Unable to load stats from {}".format(rfilename))
-                if self._stats.ndim == 1:
-                    self._stats = self._sanitized(self._stats)
+                if self._h_stats.ndim == 1:
+                    self._h_stats = self._sanitized(self._h_stats)
         elif kwargs:
             raise TypeError("Invalid keyword arguments: {}".format(tuple(kwargs)))
         super().__init__()
@@ -102,9 +109,51 @@ class Standardize(PostProcessor):
             )
         return second
 
+    # ---- where the statistics live -------------------------------------------------------
+    @property
+    def _stats(self) -> Optional[np.ndarray]:
+        """Host view of the statistics; copies them back from the GPU (one sync) if they moved on"""
+        if not self._host_fresh:
+            self._h_stats = self._d_stats.cpu().numpy()
+            self._host_fresh = True
+        return self._h_stats
+
+    @_stats.setter
+    def _stats(self, value) -> None:
+        self._h_stats = value
+        self._d_stats = None
+        self._host_fresh = True
+
+    def _width(self) -> Optional[int]:
+        if self._d_stats is not None:
+            return self._d_stats.shape[1]
+        return None if self._h_stats is None else self._h_stats.shape[1]
+
+    def device_stats(self, device, num_coeffs: Optional[int] = None):
+        """The float64 ``(2, C + 1)`` CUDA tensor the kernels accumulate into and read from
+
+        Created on first use (zeros, or a copy of statistics loaded from a file); afterwards every
+        ``*_device`` call and :func:`allreduce` works on it in stream order, without host syncs.
+        """
+        import torch
+
+        if self._d_stats is not None and self._d_stats.device != device:
+            self._stats = self._stats  # pull back, forget the copy on the other device
+        if self._d_stats is None:
+            if self._h_stats is not None:
+                self._d_stats = torch.from_numpy(np.ascontiguousarray(self._h_stats, np.float64)).to(device)
+            else:
+                if num_coeffs is None:
+                    raise ValueError("No stats have been accumulated")
+                self._d_stats = torch.zeros((2, num_coeffs + 1), dtype=torch.float64, device=device)
+            self._d_flag = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._d_stats
+
     @property
     def have_stats(self) -> bool:
-        return self._stats is not None and self._stats[0, -1]
+        if self._rows_seen:
+            return True
+        return bool(self._h_stats is not None and self._h_stats[0, -1])
 
     @property
     def stats(self) -> Optional[np.ndarray]:
@@ -112,16 +161,27 @@ class Standardize(PostProcessor):
         return self._stats
 
     def _check_width(self, num_coeffs: int) -> None:
-        if self._stats is not None and self._stats.shape[1] != num_coeffs + 1:
+        width = self._width()
+        if width is not None and width != num_coeffs + 1:
             raise ValueError(
-                "Expected feature vector of length {}; got {}".format(
-                    self._stats.shape[1] - 1, num_coeffs
-                )
+                "Expected feature vector of length {}; got {}".format(width - 1, num_coeffs)
             )
+
+    def check_zero_variance(self) -> bool:
+        """Raise the reference's "0 variance" warning if a device-side apply replaced a variance by
+        1 since the last check.  The ``*_device`` methods never read the flag themselves (that would
+        be a host sync per call); the NumPy ``apply`` and the batch pipelines call this at the end."""
+        if self._d_flag is None:
+            return False
+        hit = bool(int(self._d_flag.item()))
+        if hit:
+            self._d_flag.zero_()
+            warnings.warn("0 variance encountered. Replacing with 1")
+        return hit
 
     # ---- device-resident variants ------------------------------------------------------
     def accumulate_device(self, feats) -> None:
-        """Add the rows of a ``(rows, C)`` float32 CUDA tensor to the statistics"""
+        """Add the rows of a ``(rows, C)`` float32 CUDA tensor to the statistics (no host sync)"""
         import torch
 
         from ._gpu import stream_ptr
@@ -131,25 +191,26 @@ class Standardize(PostProcessor):
         if rows == 0:
             raise ValueError("Cannot accumulate from empty array")
         self._check_width(cols)
+        d_stats = self.device_stats(feats.device, cols)
         if isinstance(feats, LazyDeltas):
             # Deltas -> Standardize: statistics straight from the static features, the deltas are
             # recomputed on the fly instead of being written and read back
-            d_stats = torch.zeros((2, cols + 1), dtype=torch.float64, device=feats.device)
-            if feats.fused_call("pds_deltas_cmvn_accumulate", d_stats.data_ptr()):
-                partial = d_stats.cpu().numpy()
-                self._stats = partial if self._stats is None else self._stats + partial
-                return
-            feats = feats.materialize()
-        feats = feats.contiguous()
-        d_stats = torch.zeros((2, cols + 1), dtype=torch.float64, device=feats.device)
-        with torch.cuda.device(feats.device):
-            check(get_lib().pds_cmvn_accumulate(feats.data_ptr(), rows, cols, d_stats.data_ptr(),
-                                                stream_ptr(feats.device)))
-        partial = d_stats.cpu().numpy()
-        self._stats = partial if self._stats is None else self._stats + partial
+            if not feats.fused_call("pds_deltas_cmvn_accumulate", d_stats.data_ptr()):
+                feats = feats.materialize()
+        if not isinstance(feats, LazyDeltas):
+            feats = feats.contiguous()
+            with torch.cuda.device(feats.device):
+                check(get_lib().pds_cmvn_accumulate(feats.data_ptr(), rows, cols, d_stats.data_ptr(),
+                                                    stream_ptr(feats.device)))
+        self._host_fresh = False
+        self._rows_seen += rows
 
     def apply_device(self, feats, out=None):
-        """Standardise a ``(rows, C)`` float32 CUDA tensor with the accumulated statistics"""
+        """Standardise a ``(rows, C)`` float32 CUDA tensor with the accumulated statistics
+
+        Stream-ordered after whatever produced the statistics (``accumulate_device``,
+        :func:`allreduce`); the zero-variance flag is left on the device, see
+        :func:`check_zero_variance`."""
         import torch
 
         from ._gpu import stream_ptr
@@ -159,46 +220,45 @@ class Standardize(PostProcessor):
         self._check_width(cols)
         if not self.have_stats:
             raise ValueError("No stats have been accumulated")
+        d_stats = self.device_stats(feats.device, cols)
         if isinstance(feats, LazyDeltas):
-            d_stats = torch.from_numpy(np.ascontiguousarray(self._stats)).to(feats.device)
-            flag = torch.zeros(1, dtype=torch.int32, device=feats.device)
             if out is None:
                 out = torch.empty((rows, cols), dtype=torch.float32, device=feats.device)
             if feats.fused_call("pds_deltas_cmvn_apply", d_stats.data_ptr(), int(self._norm_var),
-                                flag.data_ptr(), out=out):
-                if self._norm_var and int(flag.item()):
-                    warnings.warn("0 variance encountered. Replacing with 1")
+                                self._d_flag.data_ptr(), out=out):
                 return out
             feats = feats.materialize()
         feats = feats.contiguous()
         out = torch.empty_like(feats) if out is None else out
-        d_stats = torch.from_numpy(np.ascontiguousarray(self._stats)).to(feats.device)
-        flag = torch.zeros(1, dtype=torch.int32, device=feats.device)
         with torch.cuda.device(feats.device):
             check(get_lib().pds_cmvn_apply(feats.data_ptr(), out.data_ptr(), rows, cols,
-                                           d_stats.data_ptr(), int(self._norm_var), flag.data_ptr(),
+                                           d_stats.data_ptr(), int(self._norm_var), self._d_flag.data_ptr(),
                                            stream_ptr(feats.device)))
-        if self._norm_var and int(flag.item()):
-            warnings.warn("0 variance encountered. Replacing with 1")
         return out
 
     def allreduce(self, group=None) -> None:
         """Sum the statistics over all ranks of a ``torch.distributed`` process group
 
         The only collective of the whole feature pipeline: ``2 * (C + 1)`` doubles.  With the
-        NCCL backend the buffer lives on the current CUDA device and the reduction runs over
-        NVLink; with gloo (CPU tests) it stays on the host.
+        NCCL backend the device-resident statistics are reduced in place, ordered after the
+        accumulation kernels and before the apply kernels on the current stream (no host
+        round trip); with gloo (CPU tests) the host copy is reduced.
         """
         import torch
         import torch.distributed as dist
 
-        if self._stats is None:
+        if self._width() is None:
             raise ValueError("No stats have been accumulated to reduce")
-        buf = torch.from_numpy(np.ascontiguousarray(self._stats))
         if dist.get_backend(group) == "nccl":
-            buf = buf.cuda()
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-        self._stats = buf.cpu().numpy()
+            if self._d_stats is None:
+                self.device_stats(torch.device("cuda", torch.cuda.current_device()))
+            dist.all_reduce(self._d_stats, op=dist.ReduceOp.SUM, group=group)
+            self._host_fresh = False
+        else:
+            buf = torch.from_numpy(np.ascontiguousarray(self._stats))
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+            self._stats = buf.numpy()
+        self._rows_seen = max(self._rows_seen, 1)
 
     # ---- reference API -------------------------------------------------------------------
     def accumulate(self, features: np.ndarray, axis: int = -1) -> None:
@@ -217,6 +277,11 @@ class Standardize(PostProcessor):
         self.accumulate_device(torch.from_numpy(rows).to(current_device()))
 
     def apply(self, features: np.ndarray, axis: int = -1, in_place: bool = False) -> np.ndarray:
+        """``(x - mean) / std`` per coefficient along `axis`, returned as float64
+
+        The arithmetic runs in float32 on the GPU (the statistics are float64).  With
+        ``in_place=True`` and a float64 `features` the result is also written back into the
+        argument, as in the reference (``post.py:263-264``)."""
         import torch
 
         from ._gpu import current_device
@@ -237,18 +302,28 @@ class Standardize(PostProcessor):
                     "Unable to standardize the variance of a vector with no global statistics"
                 )
             warnings.warn("Standardizing a single vector to 0")
+            if in_place and features.dtype == np.float64:
+                features[...] = 0
+                return features
             return np.zeros(features.shape, dtype=np.float64)
         d_rows = torch.from_numpy(rows).to(current_device())
         if self.have_stats:
             d_out = self.apply_device(d_rows)
+            self.check_zero_variance()
         else:  # local statistics: accumulate on this tensor only, then forget them
             local = Standardize(norm_var=self._norm_var)
             local.accumulate_device(d_rows)
             d_out = local.apply_device(d_rows)
+            local.check_zero_variance()
         out = d_out.cpu().numpy().astype(np.float64)
         if is_vector:
-            return out.reshape(features.shape)
-        return np.moveaxis(out.reshape(moved_shape), -1, axis)
+            out = out.reshape(features.shape)
+        else:
+            out = np.moveaxis(out.reshape(moved_shape), -1, axis)
+        if in_place and features.dtype == np.float64:
+            features[...] = out
+            return features
+        return out
 
     def save(self, wfilename: str, key: Optional[str] = None, compress: bool = False,
              overwrite: bool = True) -> None:
