@@ -549,7 +549,7 @@ def run_ours(args, rank, local_rank, world):
             "traffic": None,
             "peak_source": f"FP32 = {prop.multi_processor_count} SMs x 128 lanes x 2 x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz "
                            f"(clock from MEASURED_PEAKS.json); HBM {hbm_peak:.0f} GB/s {peak_src}",
-            "kernel": "pds::stft_w_kernel<true, kRows13, 5>",
+            "kernel": computer.kernel_name(device) + " (dft_size 512, power, float32 samples)",
             "kernel_ms": kernel_ms,
             "algorithmic_flops_per_launch": float(frames) * FLOPS_PER_FRAME,
             "algorithmic_bytes_per_launch": int(frames * BYTES_PER_FRAME),

@@ -93,6 +93,8 @@ int pds_stft_tile_frames(const pds_stft_plan* plan);
 /* 1 if the plan runs the shared-memory FFT kernel, 0 if it runs the generic direct-DFT kernel
  * (non power-of-two dft_size, dft_size outside [256, 2048]). */
 int pds_stft_is_fast_path(const pds_stft_plan* plan);
+/* Name of the kernel pds_stft_run launches for samples of `sig_dtype` (for benchmark records). */
+const char* pds_stft_kernel_name(const pds_stft_plan* plan, int sig_dtype);
 
 /* Frame count of a signal: 0 if sig_len < L/2 + 1 else (sig_len + S/2) / S  (compute.py:580-596) */
 int64_t pds_stft_num_frames(const pds_stft_plan* plan, int64_t sig_len);

@@ -102,6 +102,7 @@ _SIGNATURES = {
     "pds_stft_num_coeffs": (ctypes.c_int, [_vp]),
     "pds_stft_tile_frames": (ctypes.c_int, [_vp]),
     "pds_stft_is_fast_path": (ctypes.c_int, [_vp]),
+    "pds_stft_kernel_name": (ctypes.c_char_p, [_vp, ctypes.c_int]),
     "pds_stft_num_frames": (ctypes.c_int64, [_vp, ctypes.c_int64]),
     "pds_stft_layout": (
         ctypes.c_int,

@@ -5,17 +5,27 @@ Flags, file formats, return codes and the seeding contract are the reference's
 utterance at a time through a ``DataLoader`` of CPU workers.  Here reader threads decode the
 signals, utterances are packed into batches of ``--batch-samples`` samples and each batch goes
 through :class:`..pipeline.FeaturePipeline` (one fused launch per batch, copies overlapped with
-compute); the main thread writes the per-utterance ``.pt`` files and appends to the manifest only
+compute); writer threads store the per-utterance ``.pt`` files and append to the manifest only
 after a file is on disk, so an interrupted run resumes exactly like the reference's.
+
+Several GPUs: launched under ``torchrun`` (``python -m torch.distributed.run --nproc-per-node N -m
+pydrobert_speech_b200.command_line signals-to-torch-feat-dir ...``) every rank takes a shard of
+the utterances (``pipeline.shard_utterances`` on the file sizes), computes it on its own GPU and
+writes its own files; there is no data-path communication.  The reference's counterpart is
+``DataLoader(num_workers=N)`` (``command_line.py:585-594``).
 
 ``--seed`` determinism: the dither stream is keyed by ``(seed, utterance index in the map,
 sample)``, the batched analogue of the reference's ``torch.manual_seed(seed + idx)``; results do
-not depend on ``--num-workers`` or on the batch size.
+not depend on ``--num-workers``, on the batch size or on the number of ranks.
 """
 
 import argparse
+import collections
+import json
 import os
 import sys
+import threading
+import time
 
 from concurrent.futures import ThreadPoolExecutor
 from typing import Optional, Sequence
@@ -132,6 +142,9 @@ def _signals_to_torch_feat_dir_parse_args(args):
                         "ones appended, so that an interrupted run can be resumed")
     parser.add_argument("--batch-samples", type=_nonneg_int_type, default=1 << 24,
                         help="Samples per GPU batch (an implementation knob of this build)")
+    parser.add_argument("--report", default=None,
+                        help="Append one JSON line of throughput figures (files/s, audio-hours/s including "
+                        "decoding and torch.save) to this file (an addition of this build)")
     return parser.parse_args(args)
 
 
@@ -172,12 +185,32 @@ def signals_to_torch_feat_dir(args: Optional[Sequence[str]] = None) -> int:
                 line_no + 1, options.map.name, fields[0]), file=sys.stderr)
             return 1
         utt2path[fields[0]] = " ".join(fields[1:])
-    # the dither stream is keyed by the position in the *full* map, before the manifest filter
+    # the dither stream is keyed by the position in the *full* map, before the manifest filter and
+    # before sharding: the features do not depend on --num-workers, on the batch size, on which
+    # utterances were already done, or on the number of GPUs
     utt_index = {utt: idx for idx, utt in enumerate(utt2path)}
+    done = set()
     if options.manifest is not None:
         options.manifest.seek(0)
-        for line in options.manifest:
-            utt2path.pop(line.strip(), None)
+        done = {line.strip() for line in options.manifest}
+
+    # ---- one process per GPU under torchrun: every rank takes a shard of the utterances ----------
+    rank, world, local_rank = _dist_env()
+    if world > 1 and options.seed is None and options.preprocess:
+        print("--seed must be given when pre-processing on more than one rank (every rank would "
+              "draw a seed of its own)", file=sys.stderr)
+        return 1
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local_rank % max(1, torch.cuda.device_count()))
+    items = list(utt2path.items())
+    if world > 1:
+        # the shards are cut from the FULL map, before the manifest filter: every rank derives the
+        # same partition no matter what the other ranks have already appended to the manifest
+        from .pipeline import shard_utterances
+
+        sizes = [_path_size(path) for _, path in items]
+        items = [items[i] for i in shard_utterances(sizes, world)[rank]]
+    items = [item for item in items if item[0] not in done]
 
     computer = None
     if options.computer_config is not None:
@@ -197,23 +230,30 @@ def signals_to_torch_feat_dir(args: Optional[Sequence[str]] = None) -> int:
     def load(item):
         utt_id, path = item
         try:
-            signal = read_signal(path, dtype=np.float64, force_as=options.force_as, key=utt_id)
+            # native sample type: 16-bit PCM goes to the GPU as it is (the reference's float64 copy of
+            # it holds the same values); everything else is computed in float32 anyway
+            signal = read_signal(path, dtype=None, force_as=options.force_as, key=utt_id)
+            if signal.dtype != np.int16:
+                signal = signal.astype(np.float32 if pipeline is not None else np.float64, copy=False)
+            elif pipeline is None:
+                signal = signal.astype(np.float64)
         except Exception as e:
             raise IOError(f"Utterance {utt_id}: {e}") from e
         return _select_channel(signal, options.channel, utt_id)
 
     os.makedirs(options.dir, exist_ok=True)
+    manifest_lock = threading.Lock()
+    stats = dict(utterances=0, samples=0, frames=0)
 
     def write(utt_id, feats):
         torch.save(torch.as_tensor(np.ascontiguousarray(feats)).float(),
                    os.path.join(options.dir, options.file_prefix + utt_id + options.file_suffix))
         if options.manifest is not None:
-            print(utt_id, file=options.manifest)
-            options.manifest.flush()
+            with manifest_lock:  # one short line per write(2) on an O_APPEND file: safe across ranks too
+                options.manifest.write(utt_id + "\n")
+                options.manifest.flush()
 
-    def flush(batch):
-        if not batch:
-            return
+    def compute(batch):
         utts, signals = zip(*batch)
         if pipeline is None:
             # raw passthrough (S, 1); pre-processors seeded per utterance like the reference
@@ -228,29 +268,92 @@ def signals_to_torch_feat_dir(args: Optional[Sequence[str]] = None) -> int:
                 for mod in mods:
                     tensor = mod(tensor)
                 outs.append(tensor.unsqueeze(1).numpy())
-        else:
-            # every utterance keeps the dither stream of its position in the map
-            outs = []
-            run_start = 0
-            for i in range(1, len(utts) + 1):
-                if i == len(utts) or utt_index[utts[i]] != utt_index[utts[i - 1]] + 1:
-                    outs.extend(pipeline.run_list(signals[run_start:i], utt_base=utt_index[utts[run_start]]))
-                    run_start = i
-        for utt_id, feats in zip(utts, outs):
-            write(utt_id, feats)
+            return utts, outs
+        # every utterance keeps the dither stream of its position in the map
+        outs = []
+        run_start = 0
+        for i in range(1, len(utts) + 1):
+            if i == len(utts) or utt_index[utts[i]] != utt_index[utts[i - 1]] + 1:
+                outs.extend(pipeline.run_list(signals[run_start:i], utt_base=utt_index[utts[run_start]]))
+                run_start = i
+        return utts, outs
 
-    items = list(utt2path.items())
+    # Decoder threads run at most two batches ahead of the GPU (a sliding window of futures: the
+    # decoded signals of a large corpus must not pile up in host memory), torch.save runs on writer
+    # threads so that the GPU batch of the next utterances never waits for the file system.
     workers = max(1, options.num_workers)
-    batch, batch_samples = [], 0
-    with ThreadPoolExecutor(workers) as pool:
-        for item, signal in zip(items, pool.map(load, items)):
+    budget = 2 * max(1, options.batch_samples)
+    t_begin = time.perf_counter()
+    pending_writes = collections.deque()
+    with ThreadPoolExecutor(workers) as readers, ThreadPoolExecutor(max(2, workers)) as writers:
+        window = collections.deque()  # (item, future, size estimate)
+        in_flight = 0
+        position = 0
+        batch, batch_samples = [], 0
+
+        def drain_writes(limit):
+            while len(pending_writes) > limit:
+                pending_writes.popleft().result()
+
+        def flush():
+            nonlocal batch, batch_samples
+            if batch:
+                utts, outs = compute(batch)
+                for utt_id, feats in zip(utts, outs):
+                    stats["frames"] += len(feats)
+                    pending_writes.append(writers.submit(write, utt_id, feats))
+                drain_writes(4096)
+            batch, batch_samples = [], 0
+
+        while position < len(items) or window:
+            while position < len(items) and (in_flight < budget or len(window) < workers):
+                item = items[position]
+                estimate = max(1, _path_size(item[1]) // 2)
+                window.append((item, readers.submit(load, item), estimate))
+                in_flight += estimate
+                position += 1
+            item, future, estimate = window.popleft()
+            signal = future.result()
+            in_flight -= estimate
             batch.append((item[0], signal))
             batch_samples += len(signal)
+            stats["utterances"] += 1
+            stats["samples"] += len(signal)
             if batch_samples >= max(1, options.batch_samples):
-                flush(batch)
-                batch, batch_samples = [], 0
-        flush(batch)
+                flush()
+        flush()
+        drain_writes(0)
+    if options.report is not None:
+        elapsed = time.perf_counter() - t_begin
+        rate = float(computer.sampling_rate) if computer is not None else 16000.0
+        line = dict(rank=rank, world_size=world, seconds=elapsed, utterances=stats["utterances"],
+                    files_per_second=stats["utterances"] / elapsed if elapsed else None,
+                    audio_hours=stats["samples"] / rate / 3600.0,
+                    audio_hours_per_second=stats["samples"] / rate / 3600.0 / elapsed if elapsed else None,
+                    frames=stats["frames"])
+        with open(options.report, "a") as handle:
+            handle.write(json.dumps(line) + "\n")
     return 0
+
+
+def _dist_env():
+    """(rank, world size, local rank) of a torchrun / torch.distributed.run launch, else (0, 1, 0)"""
+    try:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        rank = int(os.environ.get("RANK", "0"))
+        local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    except ValueError:
+        return 0, 1, 0
+    if world < 1 or not 0 <= rank < world:
+        return 0, 1, 0
+    return rank, world, local_rank
+
+
+def _path_size(path: str) -> int:
+    try:
+        return os.path.getsize(path)
+    except OSError:
+        return 1
 
 
 # ----------------------------------------------------------------------------------------------

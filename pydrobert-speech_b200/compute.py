@@ -389,6 +389,15 @@ class ShortTimeFourierTransformFrameComputer(LinearFilterBankFrameComputer):
         self._plans[key] = plan
         return plan
 
+    def kernel_name(self, device=None, dtype=np.float32) -> str:
+        """Which kernel ``run_batch`` launches on `device` for samples of `dtype` (benchmark records)"""
+        from ._gpu import current_device
+        from ._lib import get_lib
+
+        plan = self._plan(current_device() if device is None else device)
+        code = 1 if np.dtype(dtype) == np.int16 else 0
+        return get_lib().pds_stft_kernel_name(plan.handle, code).decode()
+
     def plan_batch(self, offsets: np.ndarray, lengths: np.ndarray, device=None, utt_base: int = 0) -> "BatchLayout":
         """Work list for a packed batch: frame offsets on the host, tile table in HBM
 

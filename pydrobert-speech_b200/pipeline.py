@@ -334,20 +334,96 @@ class FeaturePipeline:
         is_stft = isinstance(self.computer, ShortTimeFourierTransformFrameComputer)
         if self._host_pre:
             signals = [self._apply_host_pre(s.astype(np.float64)) for s in signals]
+        # 16-bit PCM (what wav files hold) stays 16-bit all the way to the kernel: half the bytes
+        # over PCIe, and the conversion to float32 is exact
         all_pcm = bool(signals) and all(s.dtype == np.int16 for s in signals)
-        dtype = np.int16 if (all_pcm and is_stft) else np.float32
+        dtype = np.int16 if (all_pcm and is_stft and not self._host_pre) else np.float32
         lead = self.computer.pad_left % 4 if is_stft else 0
-        packed = PackedSignals.pack(signals, dtype, lead)
+        packed = self._pack_pinned(signals, dtype, lead)
+        counts = [self.computer.num_frames(len(s)) for s in signals]
+        out = self._pinned("out", np.float32, int(sum(counts)) * self.num_coeffs)
+        out = out[: int(sum(counts)) * self.num_coeffs].reshape(int(sum(counts)), self.num_coeffs)
         saved = self._host_pre, self._host_post
         self._host_pre, self._host_post = [], []
         try:
-            feats, frame_off = self.run_host(packed, utt_base=utt_base)
+            feats, frame_off = self.run_host(packed, out=out, utt_base=utt_base)
         finally:
             self._host_pre, self._host_post = saved
+        feats = feats.copy()  # the pinned buffer is reused by the next batch
         per_utt = [feats[frame_off[u] : frame_off[u + 1]] for u in range(len(signals))]
         for p in self._host_post:
             per_utt = [p.apply(f) if len(f) else f for f in per_utt]
         return per_utt
+
+    def _pinned(self, name: str, dtype, count: int) -> np.ndarray:
+        """A reusable page-locked host buffer of at least `count` elements (grown geometrically):
+        copies to and from it run at PCIe speed and overlap with the kernels"""
+        import torch
+
+        cache = self.__dict__.setdefault("_pinned_buffers", {})
+        key = (name, np.dtype(dtype).name)
+        buf = cache.get(key)
+        if buf is None or buf.numel() < count:
+            size = max(int(count * 1.25), 1 << 16)
+            try:
+                buf = torch.empty(size, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+            except RuntimeError:  # pinning refused (ulimit): pageable memory still works
+                buf = torch.empty(size, dtype=getattr(torch, np.dtype(dtype).name))
+            cache[key] = buf
+        return buf.numpy()
+
+    def _pack_pinned(self, signals, dtype, lead: int) -> PackedSignals:
+        lengths = np.array([len(s) for s in signals], dtype=np.int64)
+        offsets, total = PackedSignals.layout(lengths, lead)
+        data = self._pinned("in", dtype, total)[:total]
+        for sig, off, n in zip(signals, offsets, lengths):
+            data[off : off + n] = sig
+            data[off + n : off + (n + 3) // 4 * 4] = 0  # the padding must stay finite
+        data[:lead] = 0
+        data[total - 4 :] = 0
+        return PackedSignals(data, offsets, lengths)
+
+    # ---- corpus-level chain with a CMVN all-reduce ----------------------------------------
+    def run_corpus(self, packed: PackedSignals, cmvn: Optional[Standardize] = None, deltas: Optional[Deltas] = None,
+                   group=None, device=None, utt_base: int = 0):
+        """BASELINE config 5 on this rank's shard of a corpus: features (+ `deltas` along time),
+        per-coefficient statistics over ALL ranks of `group`, standardised features.
+
+        Every rank calls this with its own utterances (``shard_utterances``).  The static features
+        stay resident in HBM; the statistics are accumulated on the GPU, summed with one
+        ``all_reduce`` over NCCL in stream order, and applied -- the only host synchronisation is
+        the final copy of the result.  Returns ``(feats, frame_off)`` on the host; `cmvn` (created
+        if None) holds the global statistics afterwards, e.g. for ``cmvn.save``.
+        """
+        import torch
+
+        from ._gpu import current_device
+
+        device = current_device() if device is None else device
+        if self._host_pre or self._host_post or self._device_post:
+            raise NotImplementedError("run_corpus takes its post-processors as arguments")
+        cmvn = Standardize() if cmvn is None else cmvn
+        d_signal = torch.from_numpy(packed.data).to(device, non_blocking=True)
+        static, frame_off = self.run_device(d_signal, packed.offsets, packed.lengths, utt_base)
+        rows = int(frame_off[-1])
+        distributed = group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())
+        source = static
+        if deltas is not None:
+            row_off = torch.from_numpy(np.ascontiguousarray(frame_off)).to(device, non_blocking=True)
+            source = deltas.lazy_device(static, row_off)
+        if rows:
+            cmvn.accumulate_device(source)
+        elif distributed:
+            cmvn.device_stats(device, source.shape[1])  # an empty shard still takes part in the reduction
+        if distributed:
+            cmvn.allreduce(group)
+        width = source.shape[1]
+        out = np.empty((rows, width), dtype=np.float32)
+        if rows:
+            normed = cmvn.apply_device(source)
+            torch.from_numpy(out).copy_(normed)
+            cmvn.check_zero_variance()
+        return out, frame_off
 
     def _apply_host_pre(self, signal):
         for p in self._host_pre:

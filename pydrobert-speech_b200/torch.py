@@ -183,14 +183,28 @@ class PyTorchShortTimeFourierTransformFrameComputer(torch.nn.Module):
         self.offsets, self.centered = tuple(offsets), frame_style == "centered"
         self.dft_size, self.use_log, self.use_power = dft_size, use_log, use_power
         self.kaldi_shift, self.is_real, self.include_energy = kaldi_shift, is_real, include_energy
+        self._frame_style = frame_style
+        # Same parameter names as the reference (torch.py:362-366: ``filters.<i>`` and ``window``), so
+        # its state_dicts load here and ours load there.  They do not require gradients: the kernels
+        # are inference only (see forward()).
+        self.filters = torch.nn.ParameterList(
+            [torch.nn.Parameter(torch.as_tensor(f).clone(), requires_grad=False) for f in filters])
+        if window is None:
+            self.register_parameter("window", None)
+        else:
+            self.window = torch.nn.Parameter(window.detach().clone(), requires_grad=False)
+        self._computer = None
+        self._rebuild()
+        self.register_load_state_dict_post_hook(lambda module, _: module._rebuild())
+
+    def _rebuild(self) -> None:
+        """(Re)build the kernel plan from the current parameters (construction, load_state_dict)"""
+        window = None if self.window is None else self.window.detach().cpu().double().numpy()
         self._computer = STFTFrameComputer.from_tables(
-            offsets, filters, frame_length, frame_shift, frame_style,
-            None if window is None else window.detach().cpu().double().numpy(),
-            dft_size, use_log, use_power, include_energy, kaldi_shift, is_real,
+            list(self.offsets), [f.detach().cpu().numpy() for f in self.filters], self.frame_length,
+            self.frame_shift, self._frame_style, window, self.dft_size, self.use_log, self.use_power,
+            self.include_energy, self.kaldi_shift, self.is_real,
         )
-        # kept as buffers for state_dict compatibility; the kernels read the plan's own copies
-        self.filters = [torch.as_tensor(f) for f in filters]
-        self.register_buffer("window", None if window is None else window.detach().clone())
 
     @classmethod
     def from_stft_frame_computer(
@@ -212,18 +226,24 @@ class PyTorchShortTimeFourierTransformFrameComputer(torch.nn.Module):
         self.dft_size, self.use_log, self.use_power = computer._dft_size, computer._log, computer._power
         self.kaldi_shift, self.is_real = computer._kaldi_shift, computer._real
         self.include_energy = computer._include_energy
+        self._frame_style = computer.frame_style
+        self.filters = torch.nn.ParameterList([torch.nn.Parameter(x, requires_grad=False) for _, x in pairs])
+        self.window = torch.nn.Parameter(torch.as_tensor(computer._window).to(window_type), requires_grad=False)
         self._computer = computer  # full-precision tables: no float32/complex64 round trip
-        self.filters = [x for _, x in pairs]
-        self.register_buffer("window", torch.as_tensor(computer._window).to(window_type))
+        self.register_load_state_dict_post_hook(lambda module, _: module._rebuild())
         return self
 
     def forward(self, signal: torch.Tensor) -> torch.Tensor:
         computer = self._computer
         if signal.ndim != 1:
             raise RuntimeError(f"Expected x to be 1-dimensional; got {signal.ndim}")
+        if signal.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError(
+                "the B200 kernels are inference only: no gradient flows through "
+                "PyTorchSTFTFrameComputer; detach() the signal or run under torch.no_grad()")
         if signal.size(0) < self.frame_length // 2 + 1:
-            # (the reference forgets the energy column here, torch.py:179-180; we keep the width)
-            return signal.new_empty((0, computer.num_coeffs))
+            # like the reference (torch.py:179-180): num_filts columns, without the energy column
+            return signal.new_empty((0, len(self.offsets)))
         d_sig, home = _on_device(signal)
         if d_sig.dtype not in (torch.float32, torch.int16):
             d_sig = d_sig.float()

@@ -186,3 +186,16 @@ WINDOW_CASES = (
     ({"name": "gamma", "order": 1, "peak": 0.5}, 100),
     ("hann", 1),
 )
+
+# ---- round 2 (extra.npz) ----------------------------------------------------------------------
+SI_GABOR_41 = {"name": "si", "bank": {"name": "gabor", "scaling_function": "mel", "num_filts": 41}}  # BASELINE config 4
+C4_SEED, C4_SAMPLES = 77, 60 * 16000  # one 60 s utterance
+
+# post.Stack: (name, constructor kwargs, axis passed to apply)
+STACK_CASES = [
+    ("k3", dict(num_vectors=3), -1),
+    ("k4_edge", dict(num_vectors=4, pad_mode="edge"), -1),
+    ("k5_const", dict(num_vectors=5, pad_mode="constant", constant_values=2.0), 1),
+    ("k1", dict(num_vectors=1), -1),
+    ("k2_time1", dict(num_vectors=2, time_axis=1), 0),
+]

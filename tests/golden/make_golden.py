@@ -4,7 +4,8 @@ Run in the build container (the reference is importable there, not on the GPU bo
 
     python tests/golden/make_golden.py
 
-Outputs (committed): ``stft.npz``, ``si.npz``, ``banks.npz``, ``post.npz``, ``kaldi.npz``.
+Outputs (committed): ``stft.npz``, ``si.npz``, ``banks.npz``, ``post.npz``, ``kaldi.npz``, ``extra.npz``
+(``python tests/golden/make_golden.py extra`` rebuilds the last one alone).
 The reference's numpy path is used (``config.USE_FFTPACK = False``); its scipy.fftpack branch
 is pinned to it by the reference's own tests.  Nothing here is imported at test time except
 ``cases.py``.
@@ -171,12 +172,38 @@ def kaldi_goldens():
     np.savez_compressed(os.path.join(HERE, "kaldi.npz"), **out)
 
 
+def extra_goldens():
+    """Round-2 additions (``extra.npz``): BASELINE config 1 at its full size (all of extras/test.wav:
+    149 940 samples -> 937 x 41), one 60 s utterance of config 4 (SI + Gabor-41), ``post.Stack``"""
+    out = {}
+    with wave.open(os.path.join(REF, "extras", "test.wav")) as handle:
+        wav = np.frombuffer(handle.readframes(handle.getnframes()), dtype="<i2")
+    out["c1/signal"] = wav
+    computer = build(compute.FrameComputer, cases.README_FBANK)
+    out["c1/feats"] = computer.compute_full(wav.astype(np.float64)).astype(np.float32)
+    lin = build(compute.FrameComputer, dict(cases.README_FBANK, use_log=False))
+    out["c1/feats_linear"] = lin.compute_full(wav.astype(np.float64))
+    si = build(compute.FrameComputer, cases.SI_GABOR_41)
+    signal = (np.random.default_rng(cases.C4_SEED).standard_normal(cases.C4_SAMPLES) * 1000.0).astype(np.float32)
+    out["c4_60s/feats"] = si.compute_full(signal.astype(np.float64)).astype(np.float32)
+    rng = np.random.default_rng(41)
+    feats = rng.standard_normal((23, 5))
+    out["stack/feats"] = feats
+    for name, kwargs, axis in cases.STACK_CASES:
+        out["stack/" + name] = post.Stack(**kwargs).apply(feats, axis=axis)
+    np.savez_compressed(os.path.join(HERE, "extra.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        extra_goldens()
+        sys.exit(0)
     stft_goldens()
     si_goldens()
     bank_goldens()
     post_goldens()
     kaldi_goldens()
+    extra_goldens()
     for name in sorted(os.listdir(HERE)):
         if name.endswith(".npz"):
             print(name, os.path.getsize(os.path.join(HERE, name)))

@@ -46,7 +46,7 @@ def test_pytorch_stft_frame_computer(speech, include_energy):
         module.window, module.dft_size, module.use_log, module.use_power, module.include_energy,
         module.kaldi_shift, module.is_real)
     assert np.allclose(exp, func.numpy(), atol=1e-4)
-    assert module(torch.zeros(10)).shape == (0, computer.num_coeffs)
+    assert module(torch.zeros(10)).shape == (0, len(module.offsets))  # as the reference, torch.py:179-180
     with pytest.raises(RuntimeError, match="1-dimensional"):
         module(torch.zeros(3, 100))
     with pytest.raises(ValueError, match="dft_size"):
@@ -187,3 +187,110 @@ def test_cli_fused_preprocessing_and_postprocessing(speech, tmp_path):
         assert np.abs(feat - want).max() <= 1e-3
     assert command_line.main(["nonsense"]) == 2
     assert command_line.signals_to_torch_feat_dir(["--help"]) == 0
+
+
+def test_cli_sharded_ranks_write_identical_files(speech, tmp_path, monkeypatch):
+    """torchrun-style launch (RANK / WORLD_SIZE / LOCAL_RANK): every rank computes a shard of the
+    map and writes its own files.  With the same --seed the files of a 3-rank run are byte-identical
+    to those of a 1-rank run (the dither stream is keyed by the position in the map), every utterance
+    is written exactly once, and the shared manifest ends up complete."""
+    import torch
+
+    from pydrobert_speech_b200 import command_line
+
+    rng = np.random.default_rng(8)
+    map_path = str(tmp_path / "map")
+    with open(map_path, "w") as mp:
+        for i in range(37):
+            n = int(rng.integers(300, 9000))
+            if i % 2:
+                path = str(tmp_path / f"s{i}.wav")
+                with wave.open(path, "wb") as wv:
+                    wv.setnchannels(1)
+                    wv.setsampwidth(2)
+                    wv.setframerate(16000)
+                    wv.writeframes(rng.integers(-3000, 3000, n).astype(np.int16).tobytes())
+            else:
+                path = str(tmp_path / f"s{i}.npy")
+                np.save(path, (rng.standard_normal(n) * 500).astype(np.float32))
+            mp.write(f"utt{i:02d} {path}\n")
+    common = [map_path, json.dumps(cases.README_FBANK)]
+    tail = ["--seed=11", '--preprocess=[{"name": "dither", "coeff": 2.0}, "preemph"]', "--batch-samples=20000"]
+    single, sharded = str(tmp_path / "single"), str(tmp_path / "sharded")
+    report = str(tmp_path / "report.jsonl")
+    assert command_line.signals_to_torch_feat_dir(common + [single] + tail) == 0
+    manifest = str(tmp_path / "manifest")
+    for rank in range(3):
+        monkeypatch.setenv("WORLD_SIZE", "3")
+        monkeypatch.setenv("RANK", str(rank))
+        monkeypatch.setenv("LOCAL_RANK", "0")
+        before = set(os.listdir(sharded)) if os.path.isdir(sharded) else set()
+        assert command_line.signals_to_torch_feat_dir(
+            common + [sharded] + tail + [f"--manifest={manifest}", f"--report={report}", "--num-workers=2"]) == 0
+        written = set(os.listdir(sharded)) - before
+        assert 0 < len(written) < 37  # a proper shard, disjoint from the other ranks'
+    monkeypatch.delenv("WORLD_SIZE")
+    monkeypatch.delenv("RANK")
+    monkeypatch.delenv("LOCAL_RANK")
+    names = sorted(os.listdir(single))
+    assert names == sorted(os.listdir(sharded)) and len(names) == 37
+    for name in names:
+        a = torch.load(os.path.join(single, name))
+        b = torch.load(os.path.join(sharded, name))
+        assert a.shape == b.shape and torch.equal(a, b), name
+    with open(manifest) as f:
+        assert sorted(x.strip() for x in f) == [f"utt{i:02d}" for i in range(37)]
+    with open(report) as f:
+        lines = [json.loads(x) for x in f]
+    assert [x["rank"] for x in lines] == [0, 1, 2] and sum(x["utterances"] for x in lines) == 37
+    assert all(x["audio_hours_per_second"] > 0 and x["files_per_second"] > 0 for x in lines)
+    # without a seed a multi-rank run with dither is refused (every rank would draw its own)
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setenv("RANK", "0")
+    assert command_line.signals_to_torch_feat_dir(common + [sharded, tail[1]]) == 1
+
+
+def test_pcm_wav_goes_to_the_kernel_as_int16(speech, tmp_path):
+    """16-bit wav data is packed, copied and staged as int16 (half the PCIe bytes): same features as
+    the float32 copy of the same samples"""
+    rng = np.random.default_rng(21)
+    pcm = [rng.integers(-20000, 20000, n).astype(np.int16) for n in (5000, 16001, 777)]
+    computer = build(speech, cases.README_FBANK)
+    from pydrobert_speech_b200.pipeline import FeaturePipeline
+
+    pipe = FeaturePipeline(computer)
+    as_pcm = pipe.run_list(pcm)
+    assert pipe._pinned_buffers[("in", "int16")].numel() > 0
+    as_float = pipe.run_list([s.astype(np.float32) for s in pcm])
+    for a, b, s in zip(as_pcm, as_float, pcm):
+        assert a.shape == b.shape == (computer.num_frames(len(s)), 41)
+        assert np.array_equal(a, b)
+
+
+def test_torch_module_state_dict_is_the_references(speech):
+    """Parameter names and shapes follow the reference (torch.py:362-366: ``filters.<i>``, ``window``):
+    a state_dict saved there loads here.  Loading new values rebuilds the kernel plan."""
+    import torch
+
+    import pydrobert_speech_b200.torch as pt
+
+    computer = build(speech, cases.KALDI_FBANK)
+    module = pt.PyTorchSTFTFrameComputer.from_stft_frame_computer(computer)
+    state = module.state_dict()
+    assert sorted(state) == sorted([f"filters.{i}" for i in range(40)] + ["window"])
+    assert state["window"].shape == (400,) and state["filters.0"].dtype == torch.cfloat
+    assert all(not p.requires_grad for p in module.parameters())
+    sig = torch.randn(6000)
+    before = module(sig)
+    halved = {k: (v * 0.5 if k.startswith("filters") else v) for k, v in state.items()}
+    module.load_state_dict(halved)  # power features: filters at half amplitude = -log(4)
+    after = module(sig)
+    assert torch.allclose(after, before - float(np.log(4.0)), atol=2e-3)
+    # too short a signal: like the reference's functional form, (0, num_filts)
+    energy = pt.PyTorchSTFTFrameComputer.from_stft_frame_computer(build(speech, cases.README_FBANK))
+    assert energy(torch.zeros(10)).shape == (0, 40)
+    assert energy(torch.zeros(5000)).shape[1] == 41
+    with pytest.raises(RuntimeError, match="inference only"):
+        module(torch.randn(3000, requires_grad=True))
+    with torch.no_grad():
+        assert module(torch.randn(3000, requires_grad=True)).shape[1] == 40

@@ -242,3 +242,14 @@ def test_pipeline_matches_step_by_step(speech):
         assert feats.shape == want.shape
         if len(want):
             assert np.abs(feats - want).max() <= 1e-3
+
+
+def test_config4_sixty_second_utterance(speech, golden):
+    """BASELINE config 4 on one 60 s utterance (6000 x 41) against the reference's own output
+    (tests/golden/make_golden.py extra); the signal is regenerated from its seed"""
+    want = golden("extra")["c4_60s/feats"]
+    signal = (np.random.default_rng(cases.C4_SEED).standard_normal(cases.C4_SAMPLES) * 1000.0).astype(np.float32)
+    si = build(speech, speech.compute.FrameComputer, cases.SI_GABOR_41)
+    got = si.compute_full(signal)
+    assert got.shape == want.shape == (6000, 41)
+    assert np.abs(got - want).max() <= 1e-3

@@ -42,10 +42,25 @@ def oracle_feats(computer, signal, linear=False):
     )
 
 
-def check_linear(got, want):
+WORST = {}  # test name -> (worst floored, worst un-floored) linear relative error; printed at the end
+
+
+def check_linear(got, want, name=None):
     scale = np.maximum(np.abs(want), 1e-6 * np.abs(want).max(axis=1, keepdims=True))
     err = np.abs(got - want) / scale
+    if name is not None:  # the relaxation has a number: the error relative to each coefficient itself
+        raw = np.abs(got - want) / np.maximum(np.abs(want), np.finfo(np.float64).tiny)
+        WORST[name] = (float(err.max()), float(raw.max()))
     assert err.max() <= LIN_RTOL, f"linear relative error {err.max():.3g}"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def report_worst_linear_errors():
+    yield
+    if WORST:
+        lines = [f"  {k:28s} floored {a:.2e}   per coefficient (un-floored) {b:.2e}" for k, (a, b) in sorted(WORST.items())]
+        print("\nworst linear relative error vs the reference, per config (tolerance 1e-4 on the floored figure):\n"
+              + "\n".join(lines))
 
 
 @pytest.mark.parametrize("name", sorted(cases.STFT_CASES))
@@ -60,9 +75,24 @@ def test_matches_reference_golden(speech, golden, name):
     if cfg.get("use_log", True):
         assert np.abs(got - want).max() <= LOG_TOL
         lin = build(speech, dict(cfg, use_log=False))
-        check_linear(lin.compute_full(signal).astype(np.float64), data[name + "/feats_linear"])
+        check_linear(lin.compute_full(signal).astype(np.float64), data[name + "/feats_linear"], name)
     else:
-        check_linear(got.astype(np.float64), want)
+        check_linear(got.astype(np.float64), want, name)
+
+
+def test_config1_full_length_wav(speech, golden):
+    """BASELINE config 1 at its real size: all 149 940 samples of extras/test.wav (16-bit PCM) ->
+    937 x 41, against the reference's float64 output (tests/golden/make_golden.py extra)"""
+    data = golden("extra")
+    wav = data["c1/signal"]
+    assert wav.dtype == np.int16 and len(wav) == 149940
+    computer = build(speech, cases.README_FBANK)
+    got = computer.compute_full(wav.astype(np.float32))
+    assert got.shape == (937, 41)
+    assert np.abs(got - data["c1/feats"]).max() <= LOG_TOL
+    assert np.array_equal(got, computer.compute_batch([wav])[0])  # the int16 staging path, same bits
+    lin = build(speech, dict(cases.README_FBANK, use_log=False))
+    check_linear(lin.compute_full(wav.astype(np.float32)).astype(np.float64), data["c1/feats_linear"], "c1_full_wav")
 
 
 @pytest.mark.parametrize("n", cases.EDGE_LENGTHS)

@@ -115,3 +115,19 @@ def test_post_oracle_matches_reference(golden):
     local = oracle.cmvn_accumulate(feats)
     assert np.allclose(oracle.cmvn_apply(feats, local), data["cmvn_local"], rtol=1e-10, atol=1e-12)
     assert np.allclose(oracle.cmvn_apply(feats, local, norm_var=False), data["cmvn_applied_novar"], atol=1e-12)
+
+
+def test_stft_oracle_config1_full_wav(golden, speech):
+    """BASELINE config 1 at full size: the oracle on all of extras/test.wav (149 940 samples) against
+    the reference's 937 x 41 output (stored as float32), tables built by the package"""
+    data = golden("extra")
+    computer = speech.alias_factory_subclass_from_arg(speech.compute.FrameComputer, cases.README_FBANK)
+    got = oracle.stft_features(
+        data["c1/signal"].astype(np.float64), computer._window, computer._dft_size, computer._filt_start_idxs,
+        computer._truncated_filts, computer.frame_shift, computer.pad_left, True, True, True, True)
+    assert got.shape == (937, 41)
+    assert np.abs(got - data["c1/feats"]).max() <= 2e-6  # float32 storage of the golden
+    lin = oracle.stft_features(
+        data["c1/signal"].astype(np.float64), computer._window, computer._dft_size, computer._filt_start_idxs,
+        computer._truncated_filts, computer.frame_shift, computer.pad_left, True, True, True, True, linear=True)
+    assert np.allclose(lin, data["c1/feats_linear"], rtol=1e-11, atol=0)

@@ -17,7 +17,7 @@ from pydrobert_speech_b200.compute import PackedSignals  # noqa: E402
 cfg = {"name": "stft", "bank": "fbank", "frame_length_ms": 25, "include_energy": True,
        "pad_to_nearest_power_of_two": True, "window_function": "hanning", "use_power": True}
 n_utts = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
-variants = sys.argv[2:] or ["1", "t"]
+variants = sys.argv[2:] or ["1", "2", "p"]
 rng = np.random.default_rng(0)
 lengths = (16000 * rng.uniform(2, 20, n_utts)).astype(np.int64)
 dev = torch.device("cuda", 0)
