@@ -22,6 +22,7 @@ not depend on ``--num-workers``, on the batch size or on the number of ranks.
 import argparse
 import collections
 import json
+import logging
 import os
 import sys
 import threading
@@ -359,33 +360,18 @@ def _path_size(path: str) -> int:
 # ----------------------------------------------------------------------------------------------
 # compute-feats-from-kaldi-tables
 # ----------------------------------------------------------------------------------------------
-def compute_feats_from_kaldi_tables(args: Optional[Sequence[str]] = None) -> int:
-    """Store features from a kaldi archive in a kaldi archive
-
-    Drop-in for the reference command of the same name (``command_line.py:245-359``).  The Kaldi
-    table reader/writer and argument parser live in the optional package pydrobert-kaldi, exactly
-    as in the reference; without it this command reports the fact and returns 1.
-    """
-    import logging
-
-    try:
-        from pydrobert.kaldi.io import open as kaldi_open  # type: ignore
-        from pydrobert.kaldi.io.argparse import KaldiParser  # type: ignore
-        from pydrobert.kaldi.io.enums import KaldiDataType  # type: ignore
-        from pydrobert.kaldi.logging import register_logger_for_kaldi  # type: ignore
-    except ImportError:
-        print("compute-feats-from-kaldi-tables requires the pydrobert-kaldi package", file=sys.stderr)
-        return 1
-    logger = logging.getLogger(sys.argv[0])
-    logger.addHandler(logging.StreamHandler())
-    register_logger_for_kaldi(logger)
-    parser = KaldiParser(description=compute_feats_from_kaldi_tables.__doc__, add_verbose=True,
-                         logger=logger, formatter_class=argparse.RawDescriptionHelpFormatter,
-                         epilog=_EPILOGUE)
-    parser.add_argument("wav_rspecifier", type="kaldi_rspecifier", help="Input wave table rspecifier")
-    parser.add_argument("feats_wspecifier", type="kaldi_wspecifier", help="Output feature table wspecifier")
+def _kaldi_parse_args(args, logger):
+    """The reference builds its parser from pydrobert-kaldi's ``KaldiParser`` (``command_line.py:179-240``):
+    plain argparse plus ``-v/--verbose`` and ``--config <file>`` (one ``--option=value`` per line)"""
+    parser = argparse.ArgumentParser(
+        prog="compute-feats-from-kaldi-tables", description=compute_feats_from_kaldi_tables.__doc__,
+        formatter_class=argparse.RawDescriptionHelpFormatter, epilog=_EPILOGUE)
+    parser.add_argument("wav_rspecifier", help="Input wave table rspecifier")
+    parser.add_argument("feats_wspecifier", help="Output feature table wspecifier")
     parser.add_argument("computer_config", type=_config_type,
                         help="JSON file or string configuring the FrameComputer")
+    parser.add_argument("-v", "--verbose", type=int, default=0, help="Verbose level (higher->more logging)")
+    parser.add_argument("--config", default=None, help="File of additional '--option=value' lines")
     parser.add_argument("--min-duration", type=float, default=0.0,
                         help="Min duration of segments to process (in seconds)")
     parser.add_argument("--channel", type=int, default=-1,
@@ -393,33 +379,101 @@ def compute_feats_from_kaldi_tables(args: Optional[Sequence[str]] = None) -> int
     parser.add_argument("--preprocess", type=_config_type, default=tuple())
     parser.add_argument("--postprocess", type=_config_type, default=tuple())
     parser.add_argument("--seed", type=_nonneg_int_type, default=None)
+    parser.add_argument("--batch-samples", type=_nonneg_int_type, default=1 << 24,
+                        help="Samples per GPU batch (an implementation knob of this build)")
+    args = list(sys.argv[1:] if args is None else args)
+    for i, arg in enumerate(args):  # options of a Kaldi-style config file come first; the command line wins
+        if arg.startswith("--config="):
+            path = arg.split("=", 1)[1]
+        elif arg == "--config" and i + 1 < len(args):
+            path = args[i + 1]
+        else:
+            continue
+        with open(path) as handle:
+            extra = [line.split("#", 1)[0].strip() for line in handle]
+        args = [line for line in extra if line] + args
+        break
+    options = parser.parse_args(args)
+    logger.setLevel(logging.DEBUG if options.verbose > 0 else (logging.INFO if options.verbose == 0 else logging.WARNING))
+    return options
+
+
+def compute_feats_from_kaldi_tables(args: Optional[Sequence[str]] = None) -> int:
+    """Store features from a kaldi archive in a kaldi archive
+
+    This command is intended to replace Kaldi's (https://kaldi-asr.org/) series of
+    "compute-<something>-feats" scripts in a Kaldi pipeline.
+
+    Drop-in for the reference command of the same name (``command_line.py:245-359``): same
+    arguments, warnings and return codes.  Wave and feature tables are read and written by
+    pydrobert-kaldi when it is installed and by the built-in ``_kaldi_io`` otherwise (``ark:`` /
+    ``scp:`` files, binary or text matrices, no pipes).  Utterances are computed in batches of
+    ``--batch-samples`` samples; as in the reference the post-processors are validated but not
+    applied.
+    """
+    logger = logging.getLogger(sys.argv[0])
+    if not logger.handlers:
+        logger.addHandler(logging.StreamHandler())
     try:
-        options = parser.parse_args(args)
+        options = _kaldi_parse_args(args, logger)
     except SystemExit as ex:
         return ex.code
     from .pipeline import FeaturePipeline
 
     try:
         computer = alias_factory_subclass_from_arg(FrameComputer, options.computer_config)
+    except ValueError:
+        logger.error("Failed to build computer:", exc_info=True)
+        return 1
+    try:
         preprocessors = _build_list(PreProcessor, options.preprocess)
+    except ValueError:
+        logger.error("Failed to build preprocessor:", exc_info=True)
+        return 1
+    try:
         _build_list(PostProcessor, options.postprocess)  # validated but, as in the reference, unused
     except ValueError:
-        logger.error("Failed to build the feature pipeline:", exc_info=True)
+        logger.error("Failed to build postprocessor:", exc_info=True)
         return 1
     seed = np.random.randint(np.iinfo(np.int32).max) if options.seed is None else options.seed
-    pipeline = FeaturePipeline(computer, preprocessors, seed=seed)
+    pipeline = FeaturePipeline(computer, preprocessors, seed=seed, chunk_samples=options.batch_samples)
     try:
-        wav_reader = kaldi_open(options.wav_rspecifier, "wm", value_style="bsd")
+        from pydrobert.kaldi.io import open as kaldi_open  # type: ignore
+        from pydrobert.kaldi.io.enums import KaldiDataType  # type: ignore
+
+        open_waves = lambda spec: kaldi_open(spec, "wm", value_style="bsd")  # noqa: E731
+        open_feats = lambda spec: kaldi_open(spec, "bm", mode="w")  # noqa: E731
+        as_double = bool(KaldiDataType.BaseMatrix.is_double)
+    except ImportError:
+        from ._kaldi_io import MatrixTableWriter, WaveTableReader
+
+        open_waves, open_feats, as_double = WaveTableReader, MatrixTableWriter, False
+    try:
+        wav_reader = open_waves(options.wav_rspecifier)
     except IOError:
         logger.error("Could not read the wave table {}".format(options.wav_rspecifier))
         return 1
     try:
-        feat_writer = kaldi_open(options.feats_wspecifier, "bm", mode="w")
+        feat_writer = open_feats(options.feats_wspecifier)
     except IOError:
         logger.error("Could not open the feat table {} for writing".format(options.feats_wspecifier))
         return 1
     num_utts, num_success = 0, 0
-    for utt_id, (buff, samp_freq, duration) in list(wav_reader.items()):
+    batch, batch_samples = [], 0  # (utt_id, position in the table, signal)
+
+    def flush():
+        nonlocal batch, batch_samples, num_success
+        run_start = 0
+        for i in range(1, len(batch) + 1):  # runs of consecutive positions keep their dither streams
+            if i == len(batch) or batch[i][1] != batch[i - 1][1] + 1:
+                feats = pipeline.run_list([sig for _, _, sig in batch[run_start:i]], utt_base=batch[run_start][1])
+                for (utt_id, _, _), feat in zip(batch[run_start:i], feats):
+                    feat_writer.write(utt_id, feat.astype(np.float64) if as_double else feat)
+                    num_success += 1
+                run_start = i
+        batch, batch_samples = [], 0
+
+    for utt_id, (buff, samp_freq, duration) in wav_reader.items():
         num_utts += 1
         if duration < options.min_duration:
             logger.warning("File: {} is too short ({:.2f} sec): producing no output".format(utt_id, duration))
@@ -437,14 +491,14 @@ def compute_feats_from_kaldi_tables(args: Optional[Sequence[str]] = None) -> int
             logger.warning("File with id {} has {} channels but you specified channel {}, producing no "
                            "output".format(utt_id, buff.shape[0], channel))
             continue
-        feats = pipeline.run_list([buff[max(channel, 0)].astype(np.float64, copy=False)],
-                                  utt_base=num_utts - 1)[0]
-        if KaldiDataType.BaseMatrix.is_double:
-            feats = feats.astype(np.float64)
-        feat_writer.write(utt_id, feats)
+        signal = np.ascontiguousarray(buff[max(channel, 0)], dtype=np.float32)
+        batch.append((utt_id, num_utts - 1, signal))
+        batch_samples += len(signal)
+        if batch_samples >= max(1, options.batch_samples):
+            flush()
         if num_utts % 10 == 0:
             logger.info("Processed {} utterances".format(num_utts))
-        num_success += 1
+    flush()
     logger.info("Done {} out of {} utterances".format(num_success, num_utts))
     feat_writer.close()
     wav_reader.close()

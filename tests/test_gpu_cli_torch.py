@@ -294,3 +294,52 @@ def test_torch_module_state_dict_is_the_references(speech):
         module(torch.randn(3000, requires_grad=True))
     with torch.no_grad():
         assert module(torch.randn(3000, requires_grad=True)).shape[1] == 40
+
+
+def test_compute_feats_from_kaldi_tables(speech, tmp_path):
+    """The second drop-in command (reference command_line.py:245-359, its test
+    tests/test_command_line.py:21-86): wave scp in, float-matrix ark out, through the built-in
+    Kaldi table I/O.  Features equal compute_full; post-processors are validated but not applied
+    (as in the reference); the same --seed reproduces the dither."""
+    from pydrobert_speech_b200 import _kaldi_io as kio
+    from pydrobert_speech_b200 import command_line
+
+    rng = np.random.default_rng(5)
+    wav_scp, feat_ark = str(tmp_path / "wav.scp"), str(tmp_path / "feat.ark")
+    signals = {}
+    with open(wav_scp, "w") as scp:
+        for i in range(40):
+            utt = f"utt{i:02d}"
+            n = int(rng.integers(0, 32000))
+            pcm = rng.integers(-(2 ** 15), 2 ** 15 - 1, n).astype(np.int16)
+            path = str(tmp_path / f"{utt}.wav")
+            with wave.open(path, "wb") as wv:
+                wv.setnchannels(1)
+                wv.setsampwidth(2)
+                wv.setframerate(16000 if i != 7 else 8000)  # one file at the wrong rate: skipped
+                wv.writeframes(pcm.tobytes())
+            signals[utt] = pcm
+            scp.write(f"{utt} {path}\n")
+    cfg = str(tmp_path / "fbank.json")
+    with open(cfg, "w") as f:
+        json.dump(cases.KALDI_FBANK, f)
+    args = ["scp,s:" + wav_scp, "ark:" + feat_ark, cfg, "--postprocess=[\"unit\"]", "--batch-samples=100000"]
+    assert command_line.compute_feats_from_kaldi_tables(args) == 0
+    computer = build(speech, cases.KALDI_FBANK)
+    got = dict(kio.read_matrix_table("ark:" + feat_ark))
+    assert sorted(got) == sorted(u for u in signals if u != "utt07")
+    for utt, feat in got.items():
+        want = computer.compute_full(signals[utt].astype(np.float32))
+        assert feat.dtype == np.float32 and feat.shape == want.shape
+        assert np.array_equal(feat, want) and (feat.shape[0] == 0 or feat.shape[1] == 40)
+    # dither: --seed makes it reproducible, and it changes the features
+    noisy = args + ["--seed=30", '--preprocess=["dither"]']
+    assert command_line.main(["compute-feats-from-kaldi-tables"] + noisy) == 0
+    first = dict(kio.read_matrix_table("ark:" + feat_ark))
+    assert command_line.compute_feats_from_kaldi_tables(noisy + ["--batch-samples=30000"]) == 0
+    second = dict(kio.read_matrix_table("ark:" + feat_ark))
+    assert all(np.array_equal(first[u], second[u]) for u in first)
+    assert any(len(first[u]) and not np.array_equal(first[u], got[u]) for u in first)
+    # unreadable table / bad computer config: return code 1, no exception
+    assert command_line.compute_feats_from_kaldi_tables(["scp:" + str(tmp_path / "nope"), "ark:" + feat_ark, cfg]) == 1
+    assert command_line.compute_feats_from_kaldi_tables(["scp:" + wav_scp, "ark:" + feat_ark, '{"name": "nonsense"}']) == 1
