@@ -21,6 +21,9 @@ struct pds_stft_plan {
   // 16-frame tiles), 's' = scalar-bank kernel, 'w' = the round-1 software-pipelined kernel
   int variant = 2;
   bool want_ws = false, want_scalar = false;
+  bool blue = false;  // stft_bluestein_kernel: non-power-of-two dft_size <= 512
+  size_t blue_smem_bytes = 0;
+  int blue_grid_limit = 0;
   bool w = false;  // stft_w_kernel usable (float32 input; 16-frame tiles)
   size_t w_smem_bytes = 0;
   int w_nt = 0;
@@ -303,6 +306,14 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       plan->ws_smem_bytes = ws.total;
     }
   }
+  if (!plan->fast && !pow2 && N >= 16 && N <= kBlueM / 2 && getenv("PDS_STFT_NO_BLUESTEIN") == nullptr) {
+    const size_t blue_bytes = (size_t)blue_layout((kBlueTileFrames - 1) * S + L, L, K).total;
+    if (blue_bytes <= smem_cap) {
+      plan->blue = true;
+      plan->blue_smem_bytes = blue_bytes;
+      p.span_max = (kBlueTileFrames - 1) * S + L;
+    }
+  }
   if (!plan->fast) {
     plan->smem_bytes = sizeof(float) * (((L + 3) & ~3) + 2 * (size_t)N + ((K + 7 + 3) & ~3) + 8);
     if (plan->smem_bytes > smem_cap) {
@@ -311,7 +322,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       return PDS_ERR_UNSUPPORTED;
     }
   }
-  plan->tile_frames = plan->fast ? (N > 1024 || plan->w ? 16 : kTileFrames) : kDirectTileFrames;
+  plan->tile_frames = plan->fast ? (N > 1024 || plan->w ? 16 : kTileFrames) : (plan->blue ? kBlueTileFrames : kDirectTileFrames);
 
   // ---- build the constant tables on the host (double precision trig) --------------------
   std::vector<float> wt(std::max(wtotal, 4), 0.f);
@@ -343,6 +354,48 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     }
   }
 
+  // Bluestein tables (double precision): a[n] = window[n] conj(c[n]), c[n] = exp(i pi n^2 / N) with n^2
+  // reduced mod 2 N in integers; B = DFT_1024 of the chirp kernel b[m] = c[|m|], |m| < N, scaled by
+  // 1 / 1024 (the inverse transform's factor); and the twiddles of the 1024-point transform
+  std::vector<float2> blue_aw, blue_b, blue_tw;
+  if (plan->blue) {
+    const double pi = 3.14159265358979323846264338327950288;
+    auto chirp = [&](long long n, double* re, double* im) {
+      const long long q = (n * n) % (2LL * N);
+      const double a = pi * (double)q / (double)N;
+      *re = std::cos(a), *im = std::sin(a);
+    };
+    blue_aw.resize(L);
+    for (int n = 0; n < L; ++n) {
+      double cr, ci;
+      chirp(n, &cr, &ci);
+      blue_aw[n] = make_float2((float)(d->window[n] * cr), (float)(-(double)d->window[n] * ci));
+    }
+    std::vector<double> br(kBlueM, 0.0), bi(kBlueM, 0.0);
+    for (int m = -(N - 1); m <= N - 1; ++m) {
+      double cr, ci;
+      chirp(m < 0 ? -m : m, &cr, &ci);
+      br[(m + kBlueM) % kBlueM] = cr, bi[(m + kBlueM) % kBlueM] = ci;
+    }
+    blue_b.resize(kBlueM);
+    for (int k = 0; k < kBlueM; ++k) {  // plain O(M^2) DFT, once per plan (1 M complex multiply-adds)
+      double sr = 0.0, si = 0.0;
+      for (int m = 0; m < kBlueM; ++m) {
+        const double a = -two_pi * (double)((long long)k * m % kBlueM) / kBlueM;
+        const double wr = std::cos(a), wi = std::sin(a);
+        sr += br[m] * wr - bi[m] * wi;
+        si += br[m] * wi + bi[m] * wr;
+      }
+      blue_b[k] = make_float2((float)(sr / kBlueM), (float)(si / kBlueM));
+    }
+    blue_tw.resize(kBlueM);
+    for (int k1 = 0; k1 < 32; ++k1)
+      for (int lane = 0; lane < 32; ++lane) {
+        const double a = -two_pi * (double)(lane * k1) / kBlueM;
+        blue_tw[k1 * 32 + lane] = make_float2((float)std::cos(a), (float)std::sin(a));
+      }
+  }
+
   // ---- one device blob -----------------------------------------------------------------
   auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
   size_t o_win = 0, o_tws = align16(o_win + sizeof(float) * N);
@@ -357,7 +410,10 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   size_t o_tci = align16(o_wt + sizeof(float) * wt.size());
   size_t o_tcw = align16(o_tci + sizeof(int) * tc_items.size());
   size_t o_tcf = align16(o_tcw + sizeof(int) * tc_wstart.size());
-  size_t blob_bytes = align16(o_tcf + sizeof(float) * tc_frags.size());
+  size_t o_baw = align16(o_tcf + sizeof(float) * tc_frags.size());
+  size_t o_bb = align16(o_baw + sizeof(float2) * blue_aw.size());
+  size_t o_btw = align16(o_bb + sizeof(float2) * blue_b.size());
+  size_t blob_bytes = align16(o_btw + sizeof(float2) * blue_tw.size());
   std::vector<unsigned char> blob(blob_bytes, 0);
   std::memcpy(blob.data() + o_win, win.data(), sizeof(float) * N);
   if (!tw_stage.empty()) std::memcpy(blob.data() + o_tws, tw_stage.data(), sizeof(float2) * tw_stage.size());
@@ -372,6 +428,11 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   if (!tc_items.empty()) std::memcpy(blob.data() + o_tci, tc_items.data(), sizeof(int) * tc_items.size());
   std::memcpy(blob.data() + o_tcw, tc_wstart.data(), sizeof(int) * tc_wstart.size());
   std::memcpy(blob.data() + o_tcf, tc_frags.data(), sizeof(float) * tc_frags.size());
+  if (plan->blue) {
+    std::memcpy(blob.data() + o_baw, blue_aw.data(), sizeof(float2) * blue_aw.size());
+    std::memcpy(blob.data() + o_bb, blue_b.data(), sizeof(float2) * blue_b.size());
+    std::memcpy(blob.data() + o_btw, blue_tw.data(), sizeof(float2) * blue_tw.size());
+  }
   err = cudaMalloc(&plan->d_blob, blob_bytes);
   if (err == cudaSuccess) err = cudaMemcpy(plan->d_blob, blob.data(), blob_bytes, cudaMemcpyHostToDevice);
   if (err != cudaSuccess) {
@@ -390,6 +451,9 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   p.pair_desc = reinterpret_cast<const int4*>(base + o_desc);
   p.pair_weights = reinterpret_cast<const float*>(base + o_pwt);
   p.npairs = npairs;
+  p.blue_aw = reinterpret_cast<const float2*>(base + o_baw);
+  p.blue_b = reinterpret_cast<const float2*>(base + o_bb);
+  p.blue_tw = reinterpret_cast<const float2*>(base + o_btw);
   p.tc_items = reinterpret_cast<const int4*>(base + o_tci);
   p.tc_wstart = reinterpret_cast<const int*>(base + o_tcw);
   p.tc_frags = reinterpret_cast<const float4*>(base + o_tcf);
@@ -431,6 +495,15 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       }
     }
   }
+  for (int dt = 0; dt < 2 && plan->blue; ++dt) {
+    err = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_bluestein(plan->power, dt)),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->blue_smem_bytes);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      plan->blue = false;
+      plan->tile_frames = kDirectTileFrames;
+    }
+  }
   if (plan->w) {
     err = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_w(plan)),
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->w_smem_bytes);
@@ -454,6 +527,12 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(pick_kernel(plan, PDS_F32)),
                                                   plan->fast ? kThreads : kDirectThreads, plan->smem_bytes);
   plan->grid_limit = prop.multiProcessorCount * std::max(1, occ);
+  if (plan->blue) {
+    int occ_b = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, reinterpret_cast<const void*>(pick_bluestein(plan->power, PDS_F32)),
+                                                  kBlueThreads, plan->blue_smem_bytes);
+    plan->blue_grid_limit = prop.multiProcessorCount * std::max(1, occ_b);
+  }
   if (plan->tc) {
     int occ_tc = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tc, reinterpret_cast<const void*>(pick_tc(plan, PDS_F32)),
@@ -486,6 +565,7 @@ extern "C" const char* pds_stft_kernel_name(const pds_stft_plan* plan, int sig_d
     const bool tc2 = plan->variant == 2 && plan->N == 512;
     return tc2 ? "pds::stft_tc2_kernel" : "pds::stft_tc_kernel";
   }
+  if (plan->blue) return "pds::stft_bluestein_kernel";
   return plan->fast ? "pds::stft_fused_kernel" : "pds::stft_direct_kernel";
 }
 
@@ -591,6 +671,12 @@ extern "C" int pds_stft_run(pds_stft_plan* plan, const void* d_signal, int sig_d
     PDS_REQUIRE(n_tiles < ((int64_t)1 << 30), "at most 2^30 tiles per launch (got %lld)", (long long)n_tiles);
     const int grid = (int)std::min<int64_t>(n_tiles, plan->tc_grid_limit);
     pick_tc(plan, sig_dtype)<<<grid, kThreads, plan->tc_smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+    PDS_CUDA_CHECK(cudaGetLastError());
+    return PDS_OK;
+  }
+  if (plan->blue) {
+    const int grid = (int)std::min<int64_t>(n_tiles, plan->blue_grid_limit);
+    pick_bluestein(plan->power, sig_dtype)<<<grid, kBlueThreads, plan->blue_smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
     PDS_CUDA_CHECK(cudaGetLastError());
     return PDS_OK;
   }

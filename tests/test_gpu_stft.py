@@ -249,8 +249,10 @@ def test_host_buffer_entry_point(speech):
 
 @pytest.mark.parametrize("cfg_name", ["readme", "kaldi", "gammatone_L512", "magnitude"])
 def test_kernel_variants_match_each_other_and_oracle(speech, monkeypatch, cfg_name):
-    """The three fused kernels -- tensor-core bank (default), scalar bank (PDS_STFT_KERNEL=scalar),
-    software-pipelined (=ws) -- on a ragged batch: same features, within tolerance of the oracle"""
+    """Every fused kernel on a ragged batch -- the default (stft_tc2_kernel: tensor-core bank, phases
+    re-cut), stft_tc_kernel (PDS_STFT_KERNEL=1), the warp-specialised pipeline with 16-frame tiles
+    (=p), the scalar bank (=scalar) and the round-1 software pipeline (=ws): same features, within
+    tolerance of the oracle"""
     cfg = {
         "readme": cases.README_FBANK,
         "kaldi": cases.KALDI_FBANK,
@@ -261,21 +263,68 @@ def test_kernel_variants_match_each_other_and_oracle(speech, monkeypatch, cfg_na
     computer = build(speech, cfg)
     lengths = [0, 1, 201, 399, 5000, 16000, 33333, 160 * 32 + 240, 160 * 64 + 241, 160 * 95, 48000] * 3
     signals = [(rng.standard_normal(n) * 1000).astype(np.float32) for n in lengths]
-    monkeypatch.setenv("PDS_STFT_KERNEL", "ws")
-    ws = computer.compute_batch(signals)
-    monkeypatch.setenv("PDS_STFT_KERNEL", "scalar")
-    scalar = computer.compute_batch(signals)
-    monkeypatch.delenv("PDS_STFT_KERNEL")
-    tc = computer.compute_batch(signals)
-    for sig, a, b, c in zip(signals, ws, scalar, tc):
+    results = {}
+    for name, value in (("ws", "ws"), ("scalar", "scalar"), ("tc", "1"), ("pipe", "p"), ("tc2", None)):
+        if value is None:
+            monkeypatch.delenv("PDS_STFT_KERNEL")
+        else:
+            monkeypatch.setenv("PDS_STFT_KERNEL", value)
+        results[name] = computer.compute_batch(signals)
+    assert computer.kernel_name() == "pds::stft_tc2_kernel"
+    for i, sig in enumerate(signals):
         want = oracle_feats(computer, sig.astype(np.float64))
-        assert a.shape == want.shape == b.shape == c.shape
+        a, b = results["ws"][i], results["scalar"][i]
+        assert all(r[i].shape == want.shape for r in results.values())
         if len(want):
             assert np.allclose(a, b, rtol=2e-6, atol=2e-6)  # same math, different FMA contraction
-            # split-tf32 tensor-core bank: 2^-20 relative on sums of non-negative terms
-            assert np.allclose(c, b, rtol=5e-6, atol=5e-6)
-            for got in (a, c):
+            for name in ("tc", "pipe", "tc2"):
+                got = results[name][i]
+                # split-tf32 tensor-core bank: 2^-20 relative on sums of non-negative terms
+                assert np.allclose(got, b, rtol=5e-6, atol=5e-6), name
                 if computer._log:
                     assert np.abs(got - want).max() <= LOG_TOL
                 else:
                     check_linear(got.astype(np.float64), want)
+            assert np.array_equal(results["tc"][i], results["tc2"][i])  # same arithmetic, other phase cut
+
+
+@pytest.mark.parametrize("cfg_name", ["fbank400", "gabor320_mag", "odd_size"])
+def test_non_power_of_two_dft_bluestein(speech, monkeypatch, cfg_name):
+    """pad_to_nearest_power_of_two = false (compute.py:344-347): dft_size = frame length.  Sizes up
+    to 512 run Bluestein's algorithm on the 1024-point in-register FFT; checked against the float64
+    oracle and against the O(L K) direct-DFT kernel it replaces (PDS_STFT_NO_BLUESTEIN=1)."""
+    cfg = {
+        "fbank400": dict(cases.README_FBANK, pad_to_nearest_power_of_two=False),  # N = 400
+        "gabor320_mag": {"name": "stft", "bank": {"name": "gabor", "scaling_function": "mel", "num_filts": 30},
+                         "frame_length_ms": 20, "pad_to_nearest_power_of_two": False, "use_power": False,
+                         "use_log": False, "include_energy": True},               # N = 320
+        "odd_size": {"name": "stft", "bank": {"name": "tri", "scaling_function": "mel", "num_filts": 20}, "frame_length_ms": 20.7,
+                     "frame_shift_ms": 7.3, "pad_to_nearest_power_of_two": False, "use_power": True},  # N = 331
+    }[cfg_name]
+    rng = np.random.default_rng(17)
+    lengths = [0, 1, 250, 3000, 16000, 40000, 160 * 8 + 399, 160 * 16 + 1]
+    signals = [(rng.standard_normal(n) * 1000).astype(np.float32) for n in lengths]
+    computer = build(speech, cfg)
+    assert computer._dft_size == computer.frame_length and computer.kernel_name() == "pds::stft_bluestein_kernel"
+    got = computer.compute_batch(signals)
+    monkeypatch.setenv("PDS_STFT_NO_BLUESTEIN", "1")
+    direct_computer = build(speech, cfg)
+    assert direct_computer.kernel_name() == "pds::stft_direct_kernel"
+    direct = direct_computer.compute_batch(signals)
+    for sig, a, b in zip(signals, got, direct):
+        want = oracle_feats(computer, sig.astype(np.float64))
+        assert a.shape == want.shape == b.shape
+        if len(want):
+            if computer._log:
+                assert np.abs(a - want).max() <= LOG_TOL and np.abs(b - want).max() <= LOG_TOL
+            else:
+                check_linear(a.astype(np.float64), want, "bluestein_" + cfg_name)
+    # fused pre-processing and 16-bit input take the same staging code as every other kernel
+    pcm = rng.integers(-20000, 20000, 30000).astype(np.int16)
+    monkeypatch.delenv("PDS_STFT_NO_BLUESTEIN")
+    a = computer.compute_batch([pcm], preemph=0.97)[0]
+    want = oracle_feats(computer, oracle.preemphasize(pcm.astype(np.float64), 0.97))
+    if computer._log:
+        assert np.abs(a - want).max() <= LOG_TOL
+    else:
+        check_linear(a.astype(np.float64), want)

@@ -1,4 +1,6 @@
-"""Throughput of the fused STFT kernel at other DFT sizes (development aid)."""
+"""Device-side throughput of the fused STFT path for other DFT sizes (development aid):
+power-of-two sizes on the tensor-core kernels, non-power-of-two sizes on the Bluestein kernel and on
+the direct-DFT kernel it replaces."""
 import os
 import sys
 
@@ -11,26 +13,42 @@ from pydrobert_speech_b200.compute import PackedSignals  # noqa: E402
 
 dev = torch.device("cuda", 0)
 rng = np.random.default_rng(0)
-lengths = (16000 * rng.uniform(2, 20, 3000)).astype(np.int64)
-for ms, shift in ((16, 10), (25, 10), (32, 10), (50, 10), (64, 16), (100, 20)):
-    cfg = {"name": "stft", "bank": "fbank", "frame_length_ms": ms, "frame_shift_ms": shift, "include_energy": True,
-           "pad_to_nearest_power_of_two": True, "window_function": "hanning", "use_power": True}
-    computer = pds.alias_factory_subclass_from_arg(pds.compute.FrameComputer, cfg)
-    offsets, total = PackedSignals.layout(lengths, computer.pad_left % 4)
+
+
+def run(label, cfg, n_utts, env=None):
+    for key, value in (env or {}).items():
+        os.environ[key] = value
+    comp = pds.alias_factory_subclass_from_arg(pds.compute.FrameComputer, cfg)
+    rate = comp.sampling_rate
+    lengths = (rate * rng.uniform(2, 20, n_utts)).astype(np.int64)
+    offsets, total = PackedSignals.layout(lengths, comp.pad_left % 4)
     d_sig = torch.randn(total, device=dev) * 1000
-    layout = computer.plan_batch(offsets, lengths, dev)
-    feats = torch.empty((layout.rows, computer.num_coeffs), device=dev)
+    layout = comp.plan_batch(offsets, lengths, dev)
+    out = torch.empty((layout.rows, comp.num_coeffs), device=dev)
     for _ in range(3):
-        computer.run_batch(layout, d_sig, out=feats)
+        comp.run_batch(layout, d_sig, out=out)
     torch.cuda.synchronize()
     best = 1e9
     for _ in range(5):
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
-        computer.run_batch(layout, d_sig, out=feats)
+        comp.run_batch(layout, d_sig, out=out)
         t1.record()
         torch.cuda.synchronize()
         best = min(best, t0.elapsed_time(t1))
-    hours = lengths.sum() / 16000 / 3600
-    print(f"L={computer.frame_length} S={computer.frame_shift} N={computer._dft_size}: {best:.3f} ms  "
-          f"{hours / (best * 1e-3):.0f} audio-h/s  frames/s={layout.rows / (best * 1e-3):.3e}")
+    hours = lengths.sum() / rate / 3600
+    print(f"{label:34s} N={comp._dft_size:5d} kernel={comp.kernel_name():28s} {best:8.3f} ms  "
+          f"{layout.rows / best / 1e6:6.3f} G frames/s  {hours / (best * 1e-3):8.1f} audio-h/s", flush=True)
+    for key in (env or {}):
+        os.environ.pop(key)
+
+
+FBANK = {"name": "stft", "bank": "fbank", "frame_length_ms": 25, "include_energy": True,
+         "window_function": "hanning", "use_power": True}
+run("fbank 25 ms, padded (512)", dict(FBANK, pad_to_nearest_power_of_two=True), 2000)
+run("fbank 25 ms, not padded (400)", dict(FBANK, pad_to_nearest_power_of_two=False), 2000)
+run("  same on the direct-DFT kernel", dict(FBANK, pad_to_nearest_power_of_two=False), 200, {"PDS_STFT_NO_BLUESTEIN": "1"})
+run("fbank 20 ms, not padded (320)", dict(FBANK, frame_length_ms=20, pad_to_nearest_power_of_two=False), 2000)
+run("fbank 16 ms (256)", dict(FBANK, frame_length_ms=16), 2000)
+run("fbank 50 ms (1024)", dict(FBANK, frame_length_ms=50), 1000)
+run("fbank 100 ms (2048)", dict(FBANK, frame_length_ms=100), 500)
