@@ -724,7 +724,8 @@ class ShortIntegrationFrameComputer(LinearFilterBankFrameComputer):
 
         from ._lib import PdsSiDesc, check, get_lib
 
-        plan = self._plans.get(device.index)
+        key = (device.index, os.environ.get("PDS_SI_KERNEL", ""), float(config.LOG_FLOOR_VALUE))
+        plan = self._plans.get(key)
         if plan is not None:
             return plan
         lib = get_lib()
@@ -751,7 +752,7 @@ class ShortIntegrationFrameComputer(LinearFilterBankFrameComputer):
         check(lib.pds_si_plan_create(ctypes.byref(desc), device.index, ctypes.byref(handle)),
               "creating the SI plan")
         plan = _PlanHandle(handle, lib.pds_si_plan_destroy)
-        self._plans[device.index] = plan
+        self._plans[key] = plan
         return plan
 
     def compute_packed_device(self, d_signal, offsets: np.ndarray, lengths: np.ndarray):
