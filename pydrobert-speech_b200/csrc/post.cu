@@ -5,6 +5,7 @@
 // feature matrix; they are written for coalesced row-major access and enough resident CTAs to
 // cover HBM latency (grid sized from the SM count), not for arithmetic throughput.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -281,6 +282,172 @@ __global__ void __launch_bounds__(kDeltaThreads) deltas25_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------
+// Streaming form of the same specialisation (the default): no shared-memory staging.  A thread owns
+// one column of a run of kD25sRun consecutive rows and slides the nine samples its filters need
+// through registers: per group of eight rows it issues eight independent (coalesced: neighbouring
+// threads are neighbouring columns) loads, then 8 x (5 + 9) FMAs and the stores -- about 25
+// instructions per (row, column) against 75 in deltas25_kernel, whose load -> barrier -> compute
+// structure also left it latency bound at four CTAs per SM (ncu: issue slots 47 % busy, long
+// scoreboard 6.5 stalls per issue).  A CTA's 256 / cols runs are adjacent, so it reads and writes one
+// contiguous chunk; the persistent grid walks the chunks.  The utterance holding a chunk's first row
+// is looked up (binary search on row_off) by an otherwise idle thread while the previous chunk is in
+// work; runs then walk forward from it.  Rows within four of an utterance boundary take clamped loads.
+// ------------------------------------------------------------------------------------------
+// rows per run, measured on 10.99 M x 41 (tools/probe_post.py): the statistics pass likes long runs (fewer
+// halo reloads: 1.01 ms at 128 rows against 1.37 at 16), the storing passes short ones (a CTA's stores stay
+// close together: 1.80 ms at 16 rows against 2.31 at 128)
+constexpr int kD25sRunStats = 128, kD25sRunStore = 16;
+
+template <int MODE>
+__global__ void __launch_bounds__(kDeltaThreads, 4) deltas25s_kernel(const __grid_constant__ DeltaParams p) {
+  __shared__ long long s_utt[2];
+  extern __shared__ __align__(16) float s_dyn[];  // statistics fold (MODE 1)
+  const int tid = threadIdx.x, cols = p.cols, out_cols = 3 * cols;
+  const int runs = kDeltaThreads / cols;
+  const int run = tid / cols, c = tid - run * cols;
+  const bool worker = run < runs;
+  const int run_rows = p.rows_per_cta;  // rows per run on this path
+  const long long chunk_rows = (long long)runs * run_rows;
+  const long long n_chunks = (p.total_rows + chunk_rows - 1) / chunk_rows;
+  float f1[5], f2[9];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) f1[j] = p.taps[p.filt_off[0] + j];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) f2[j] = p.taps[p.filt_off[1] + j];
+  float scale[3] = {1.f, 1.f, 1.f}, shift[3] = {0.f, 0.f, 0.f};
+  if (MODE == kD25Apply && worker) {  // scale / shift of this thread's three output columns (post.py:264-294)
+    const double count = p.stats[out_cols];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double mean = p.stats[k * cols + c] / count;
+      double sc = 1.0;
+      if (p.norm_var) {
+        double var = p.stats[out_cols + 1 + k * cols + c] / count - mean * mean;
+        if (fabs(var) <= 1e-8) {  // np.isclose(var, 0)
+          var = 1.0;
+          if (p.zero_var) *p.zero_var = 1;
+        }
+        sc = 1.0 / sqrt(var);
+      }
+      scale[k] = (float)sc;
+      shift[k] = (float)(mean * sc);
+    }
+  }
+  double sum[3] = {0.0, 0.0, 0.0}, sq[3] = {0.0, 0.0, 0.0};
+  const float* __restrict__ in = p.in + c;
+
+  // utterance of a chunk's first row: largest u with row_off[u] <= r (skips empty utterances)
+  auto find_utt = [&](long long r) {
+    long long lo = 0, hi = p.n_utts;
+    while (hi - lo > 1) {
+      const long long mid = (lo + hi) >> 1;
+      if (p.row_off[mid] <= r) lo = mid; else hi = mid;
+    }
+    return lo;
+  };
+  const int searcher = kDeltaThreads - 1;
+  if (tid == searcher && blockIdx.x < n_chunks) s_utt[0] = find_utt((long long)blockIdx.x * chunk_rows);
+  __syncthreads();
+
+  int parity = 0;
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, parity ^= 1) {
+    const long long next = chunk + gridDim.x;
+    if (tid == searcher && next < n_chunks) s_utt[parity ^ 1] = find_utt(next * chunk_rows);
+    if (worker) {
+      const long long r_begin = chunk * chunk_rows + (long long)run * run_rows;
+      const long long r_end = min(r_begin + run_rows, p.total_rows);
+      long long u = s_utt[parity];
+      long long lo = 0, hi = -1;  // rows of the current utterance (inclusive)
+      float w[16];                // w[j] = x[r + j - 4] for the group's first row r
+      bool carried = false;
+      for (long long r = r_begin; r < r_end; r += 8) {
+        if (r > hi) {  // (re)locate the utterance of row r
+          while (p.row_off[u + 1] <= r) ++u;
+          lo = p.row_off[u], hi = p.row_off[u + 1] - 1;
+        }
+        const int n = (int)min(8LL, r_end - r);
+        const bool interior = r - 4 >= lo && r + 11 <= hi && n == 8;
+        if (interior) {
+          const float* __restrict__ src = in + (r - 4) * cols;
+          if (carried) {  // the previous group left rows r - 4 .. r + 3 in w[8..15]
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = w[j + 8];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = src[(long long)j * cols];
+          }
+#pragma unroll
+          for (int j = 8; j < 16; ++j) w[j] = src[(long long)j * cols];
+        }
+        carried = interior;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q >= n) break;
+          float d0, d1 = 0.f, d2 = 0.f;
+          if (interior) {
+            d0 = w[q + 4];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) d1 = fmaf(f1[j], w[q + 2 + j], d1);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) d2 = fmaf(f2[j], w[q + j], d2);
+          } else {
+            const long long rr = r + q;
+            if (rr > hi) {
+              while (p.row_off[u + 1] <= rr) ++u;
+              lo = p.row_off[u], hi = p.row_off[u + 1] - 1;
+            }
+            d0 = in[rr * cols];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) d1 = fmaf(f1[j], in[max(lo, min(hi, rr + j - 2)) * cols], d1);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) d2 = fmaf(f2[j], in[max(lo, min(hi, rr + j - 4)) * cols], d2);
+          }
+          if (MODE == kD25Stats) {
+            sum[0] += (double)d0, sq[0] += (double)d0 * d0;
+            sum[1] += (double)d1, sq[1] += (double)d1 * d1;
+            sum[2] += (double)d2, sq[2] += (double)d2 * d2;
+          } else {
+            float* __restrict__ dst = p.out + (r + q) * out_cols + c;
+            if (MODE == kD25Apply) {
+              __stcs(dst, fmaf(d0, scale[0], -shift[0]));
+              __stcs(dst + cols, fmaf(d1, scale[1], -shift[1]));
+              __stcs(dst + 2 * cols, fmaf(d2, scale[2], -shift[2]));
+            } else {
+              __stcs(dst, d0);
+              __stcs(dst + cols, d1);
+              __stcs(dst + 2 * cols, d2);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();  // the next chunk's utterance index is in place
+  }
+  if (MODE == kD25Stats) {
+    // fold the runs of a column through shared memory, then one atomic per column and CTA
+    double* s_red = reinterpret_cast<double*>(s_dyn);  // [runs][6][cols]
+    if (worker) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        s_red[(run * 6 + k) * cols + c] = sum[k];
+        s_red[(run * 6 + 3 + k) * cols + c] = sq[k];
+      }
+    }
+    __syncthreads();
+    if (worker && run == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double a = 0.0, b = 0.0;
+        for (int g = 0; g < runs; ++g) a += s_red[(g * 6 + k) * cols + c], b += s_red[(g * 6 + 3 + k) * cols + c];
+        atomicAdd(p.stats + k * cols + c, a);
+        atomicAdd(p.stats + (out_cols + 1) + k * cols + c, b);
+      }
+    }
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(p.stats + out_cols, (double)p.total_rows);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // CMVN statistics: per-column sum and sum of squares in float64 (post.py:175-191)
 // ------------------------------------------------------------------------------------------
 constexpr int kStatsThreadsX = 32;
@@ -517,6 +684,25 @@ int run_deltas(int mode, const float* d_in, float* d_out, int64_t total_rows, in
     const unsigned grid = mode == kD25Stats ? (unsigned)std::min<long long>(grid_x, (long long)sm_count(device) * 8)
                                             : (unsigned)grid_x;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static const bool staged = getenv("PDS_DELTAS_KERNEL") && getenv("PDS_DELTAS_KERNEL")[0] == 's';
+    if (!staged) {
+      // streaming kernel (default): persistent grid, eight CTAs per SM; dynamic shared memory only
+      // for the statistics fold
+      static const int run_env = getenv("PDS_D25_RUN") ? std::max(8, atoi(getenv("PDS_D25_RUN")) / 8 * 8) : 0;
+      static const int grid_env = getenv("PDS_D25_GRID") ? std::max(1, atoi(getenv("PDS_D25_GRID"))) : 0;
+      const int run_rows = run_env ? run_env : (mode == kD25Stats ? kD25sRunStats : kD25sRunStore);
+      const int ctas_per_sm = grid_env ? grid_env : (mode == kD25Stats ? 16 : 8);
+      p.rows_per_cta = run_rows;
+      const long long chunk_rows = (long long)(kDeltaThreads / n_cols) * run_rows;
+      const long long n_chunks = (total_rows + chunk_rows - 1) / chunk_rows;
+      const unsigned sgrid = (unsigned)std::min<long long>(n_chunks, (long long)sm_count(device) * ctas_per_sm);
+      const size_t fold = mode == kD25Stats ? sizeof(double) * 6 * (size_t)(kDeltaThreads / n_cols) * n_cols + 16 : 0;
+      if (mode == kD25Stats) deltas25s_kernel<kD25Stats><<<sgrid, kDeltaThreads, fold, st>>>(p);
+      else if (mode == kD25Apply) deltas25s_kernel<kD25Apply><<<sgrid, kDeltaThreads, fold, st>>>(p);
+      else deltas25s_kernel<kD25Store><<<sgrid, kDeltaThreads, fold, st>>>(p);
+      PDS_CUDA_CHECK(cudaGetLastError());
+      return PDS_OK;
+    }
     if (mode == kD25Stats) deltas25_kernel<kD25Stats><<<grid, kDeltaThreads, smem, st>>>(p);
     else if (mode == kD25Apply) deltas25_kernel<kD25Apply><<<grid, kDeltaThreads, smem, st>>>(p);
     else deltas25_kernel<kD25Store><<<grid, kDeltaThreads, smem, st>>>(p);
