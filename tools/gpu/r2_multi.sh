@@ -12,5 +12,5 @@ d=json.loads([l for l in open('gpurun_out/bench$N.json').read().splitlines() if 
 print('N', d['n_gpus'], 'value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], 'pcm', d['e2e']['int16_pcm_input'] and d['e2e']['int16_pcm_input']['value'])
 for k,v in d['per_config'].items(): print(k, v['value'], v['ms_per_step'], v.get('collective_us'))
 PY
-timeout 600 python tools/cli_bench.py $N 2>&1 | tail -8
+timeout 900 python tools/cli_bench.py $N ${CLI_UTTS:-2000} 2>&1 | tail -1 | tee gpurun_out/cli_bench_$N.json
 nvidia-smi topo -m | head -12 > gpurun_out/topo$N.txt
