@@ -220,7 +220,13 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
             tc_frags.push_back(l0);
             tc_frags.push_back(l1);
           }
-      for (int m0 = 0; m0 < (N > 1024 ? 16 : kTileFrames); m0 += 16) runs.push_back({8 * j, m0, blk0, nblk, frag});
+      // one item per 16-frame half -- or, when there are at least as many filter groups as warps, one
+      // item for both halves of a 32-frame tile (each weight fragment is then fetched once per tile)
+      if (N <= 1024 && n_ntiles >= n_warps && getenv("PDS_STFT_SPLIT_HALVES") == nullptr) {
+        runs.push_back({8 * j, kBothHalves, blk0, 2 * nblk, frag});
+      } else {
+        for (int m0 = 0; m0 < (N > 1024 ? 16 : kTileFrames); m0 += 16) runs.push_back({8 * j, m0, blk0, nblk, frag});
+      }
       tc_p_rows = std::max(tc_p_rows, 16 * (blk0 + nblk));
     }
     // longest-processing-time-first deal to the warps
@@ -246,7 +252,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
         const Run& r = runs[i];
         tc_items.push_back(r.n0 | (r.slot << 16));
         tc_items.push_back(r.blk0);
-        tc_items.push_back(r.nblk);
+        tc_items.push_back(r.slot == kBothHalves ? r.nblk / 2 : r.nblk);
         tc_items.push_back(r.frag);  // float4 index
       }
     }

@@ -910,6 +910,12 @@ __device__ __forceinline__ void tc_issue(const StftParams& p, const int* __restr
   }
 }
 
+// An item with this m0 covers BOTH 16-frame halves of a 32-frame tile: one fetch of a weight
+// fragment feeds two A tiles.  Used when there are at least as many filter groups as warps (dense
+// banks: gammatone-64 has 8 groups x 17 blocks = 136 KB of fragments, far beyond the L1; with one
+// item per (group, half) every tile pulled them through the L2 twice: 8.5 KB per frame).
+constexpr int kBothHalves = 0x7fff;
+
 template <int TS>
 __device__ __forceinline__ void bank_tc(int warp, int lane, const float* __restrict__ s_P,
                                         const int4* __restrict__ s_items, const int* __restrict__ s_wstart,
@@ -927,6 +933,65 @@ __device__ __forceinline__ void bank_tc(int warp, int lane, const float* __restr
   for (int it = s_wstart[warp]; it < it_end; ++it) {
     const int4 d = s_items[it];
     const int n0 = d.x & 0xffff, m0 = d.x >> 16;
+    if (m0 == kBothHalves) {
+      const float* __restrict__ pa = s_P + d.y * (16 * TS) + lane_p;
+      const float4* __restrict__ fr = frags + d.w + lane;
+      float acc[2][2][2][4];  // [half][k-step parity][main | correction][fragment]
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[m][s][q][i] = 0.f;
+      int left = d.z;  // >= 1 (host)
+      do {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const float4 f = ldg_keep(fr + 32 * s);
+          const uint32_t whi0 = __float_as_uint(f.x), whi1 = __float_as_uint(f.y);
+          const uint32_t wlo0 = __float_as_uint(f.z), wlo1 = __float_as_uint(f.w);
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            const float* __restrict__ pm = pa + 16 * m;
+            const float a[4] = {pm[(2 * s) * TS], pm[(2 * s) * TS + 8], pm[(2 * s + 1) * TS], pm[(2 * s + 1) * TS + 8]};
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              hi[i] = __float_as_uint(a[i]) & 0xffffe000u;
+              lo[i] = __float_as_uint(a[i] - __uint_as_float(hi[i]));
+            }
+            mma_tf32(acc[m][s][0], hi[0], hi[1], hi[2], hi[3], whi0, whi1);
+            mma_tf32(acc[m][s][1], lo[0], lo[1], lo[2], lo[3], whi0, whi1);
+            mma_tf32(acc[m][s][1], hi[0], hi[1], hi[2], hi[3], wlo0, wlo1);
+          }
+        }
+        pa += 16 * TS;
+        fr += 64;
+      } while (--left > 0);
+      const bool c0 = n0 + 2 * t < p.F, c1 = n0 + 2 * t + 1 < p.F;
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[i] = (acc[m][0][1][i] + acc[m][1][1][i]) + (acc[m][0][0][i] + acc[m][1][0][i]);  // small terms first
+          if (use_log) v[i] = fast_log(fmaxf(v[i], log_floor));
+        }
+        float* __restrict__ r0 = out_tile + (16 * m * C + n0 + lane_o);
+        float* __restrict__ r1 = r0 + 8 * C;
+        if (16 * m + g < nframes) {
+          if (c0) __stcs(r0, v[0]);
+          if (c1) __stcs(r0 + 1, v[1]);
+        }
+        if (16 * m + g + 8 < nframes) {
+          if (c0) __stcs(r1, v[2]);
+          if (c1) __stcs(r1 + 1, v[3]);
+        }
+      }
+      continue;
+    }
     if (m0 >= nframes) continue;
     const float* __restrict__ pa = s_P + d.y * (16 * TS) + m0 + lane_p;
     const float4* __restrict__ fr = frags + d.w + lane;
@@ -1462,7 +1527,7 @@ __global__ void __launch_bounds__(kWThreads, 1) stft_w_kernel(const __grid_const
     for (int n = 0; n < kWMaxNT; ++n) blk0[n] = 0, nblk[n] = 0;
     for (int i = 0; i < p.tc_nitems; ++i) {
       const int4 d = p.tc_items[i];
-      if ((d.x >> 16) == 0) {
+      if ((d.x >> 16) == 0 || (d.x >> 16) == kBothHalves) {
         const int n = (d.x & 0xffff) >> 3;
         blk0[n] = d.y, nblk[n] = d.z;
         s_adj[n] = d.w - d.y * 64;
