@@ -355,7 +355,8 @@ class ShortTimeFourierTransformFrameComputer(LinearFilterBankFrameComputer):
         # the kernel switch (read by the library once per plan) and the log floor are baked into a
         # plan: both are part of the key, so changing either takes effect on the next call
         key = (device.index, float(preemph), float(dither), bool(dither_first),
-               os.environ.get("PDS_STFT_KERNEL", ""), float(config.LOG_FLOOR_VALUE))
+               os.environ.get("PDS_STFT_KERNEL", ""), os.environ.get("PDS_STFT_BANK", ""),
+               float(config.LOG_FLOOR_VALUE))
         plan = self._plans.get(key)
         if plan is not None:
             return plan

@@ -24,6 +24,7 @@ struct pds_stft_plan {
   bool blue = false;  // stft_bluestein_kernel: non-power-of-two dft_size <= 512
   size_t blue_smem_bytes = 0;
   int blue_grid_limit = 0;
+  bool bf16_bank = false;  // dense bank contracted with bf16 two-term splits (fragment layout differs)
   bool w = false;  // stft_w_kernel usable (float32 input; 16-frame tiles)
   size_t w_smem_bytes = 0;
   int w_nt = 0;
@@ -66,6 +67,14 @@ KernelFn pick_tc(const pds_stft_plan* plan, int dtype) {
 }
 
 KernelFn pick_w(const pds_stft_plan* plan) { return pick_w512(plan->power, plan->row_mode, plan->w_nt); }
+
+// round-to-nearest-even conversion to bfloat16 (the upper 16 bits of the result's float pattern)
+uint32_t bf16_rn(float w) {
+  uint32_t bits;
+  std::memcpy(&bits, &w, 4);
+  bits += 0x7fffu + ((bits >> 16) & 1u);
+  return bits >> 16;
+}
 
 // round-to-nearest split of a weight into two tf32-representable terms
 void split_tf32(float w, float* hi, float* lo) {
@@ -190,6 +199,15 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   int tc_p_rows = ((K + 15) / 16) * 16;
   {
     struct Run { int n0, slot, blk0, nblk, frag; };
+    // Dense banks (at least as many filter groups as warps): one item per group covers both halves of a
+    // 32-frame tile, so that each weight fragment is fetched once per tile.
+    // Fragment type: bf16 m16n8k16 MMAs on two-term splits by default (half the MMAs and half the fragment
+    // bytes of split-tf32; relative error 3 * 2^-17 instead of 2^-20, tolerance 1e-4); PDS_STFT_BANK=tf32
+    // keeps split-tf32 m16n8k8, which stft_w_kernel and dft_size 2048 always use.
+    const bool dense = N <= 1024 && n_ntiles >= n_warps && getenv("PDS_STFT_SPLIT_HALVES") == nullptr;
+    const char* bank_env = getenv("PDS_STFT_BANK");
+    const bool dense_bf16 = N <= 1024 && plan->variant != 5 && !(bank_env && bank_env[0] == 't');
+    plan->bf16_bank = dense_bf16;
     std::vector<Run> runs;
     for (int j = 0; j < n_ntiles; ++j) {
       int lo_bin = K, hi_bin = 0;
@@ -201,7 +219,36 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
       const int blk0 = hi_bin > lo_bin ? lo_bin / 16 : 0;
       const int nblk = hi_bin > lo_bin ? (hi_bin + 15) / 16 - blk0 : 1;  // all-zero group: one block of zeros
       const int frag = (int)(tc_frags.size() / 4);
-      for (int b = blk0; b < blk0 + nblk; ++b)
+      for (int b = blk0; b < blk0 + nblk; ++b) {
+        if (dense_bf16) {
+          // bf16 m16n8k16 fragments of the whole 16-bin block: k = 2t, 2t+1, 2t+8, 2t+9 <-> bins 4t .. 4t+3;
+          // every weight as two bf16 terms (w1 = rn(w), w2 = rn(w - w1)): {b0_w1, b1_w1, b0_w2, b1_w2}
+          for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, t = lane & 3;
+            const int f = 8 * j + g;
+            uint32_t packed[2][2] = {{0u, 0u}, {0u, 0u}};  // [term][b0 | b1]
+            for (int c = 0; c < 4; ++c) {
+              const int bin = 16 * b + 4 * t + c;
+              float w = 0.f;
+              if (f < F && bin >= d->band_lo[f] && bin < d->band_lo[f] + d->band_len[f])
+                w = d->weights[d->band_off[f] + (bin - d->band_lo[f])];
+              const uint32_t w1 = bf16_rn(w);
+              float w1f;
+              const uint32_t w1bits = w1 << 16;
+              std::memcpy(&w1f, &w1bits, 4);
+              const uint32_t w2 = bf16_rn(w - w1f);
+              packed[0][c >> 1] |= w1 << (16 * (c & 1));
+              packed[1][c >> 1] |= w2 << (16 * (c & 1));
+            }
+            for (int term = 0; term < 2; ++term)
+              for (int q = 0; q < 2; ++q) {
+                float as_float;
+                std::memcpy(&as_float, &packed[term][q], 4);
+                tc_frags.push_back(as_float);
+              }
+          }
+          continue;
+        }
         for (int s2 = 0; s2 < 2; ++s2)
           for (int lane = 0; lane < 32; ++lane) {
             const int g = lane >> 2, t = lane & 3;
@@ -220,12 +267,14 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
             tc_frags.push_back(l0);
             tc_frags.push_back(l1);
           }
+      }
       // one item per 16-frame half -- or, when there are at least as many filter groups as warps, one
       // item for both halves of a 32-frame tile (each weight fragment is then fetched once per tile)
-      if (N <= 1024 && n_ntiles >= n_warps && getenv("PDS_STFT_SPLIT_HALVES") == nullptr) {
-        runs.push_back({8 * j, kBothHalves, blk0, 2 * nblk, frag});
+      if (dense) {
+        runs.push_back({8 * j, dense_bf16 ? kBothHalvesBf16 : kBothHalves, blk0, 2 * nblk, frag});
       } else {
-        for (int m0 = 0; m0 < (N > 1024 ? 16 : kTileFrames); m0 += 16) runs.push_back({8 * j, m0, blk0, nblk, frag});
+        for (int m0 = 0; m0 < (N > 1024 ? 16 : kTileFrames); m0 += 16)
+          runs.push_back({8 * j, dense_bf16 ? (m0 | kHalfBf16) : m0, blk0, nblk, frag});
       }
       tc_p_rows = std::max(tc_p_rows, 16 * (blk0 + nblk));
     }
@@ -252,7 +301,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
         const Run& r = runs[i];
         tc_items.push_back(r.n0 | (r.slot << 16));
         tc_items.push_back(r.blk0);
-        tc_items.push_back(r.slot == kBothHalves ? r.nblk / 2 : r.nblk);
+        tc_items.push_back(r.slot == kBothHalves || r.slot == kBothHalvesBf16 ? r.nblk / 2 : r.nblk);
         tc_items.push_back(r.frag);  // float4 index
       }
     }
@@ -295,7 +344,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     }
     // warp-specialised kernel: dft_size 512, no fused pre-processing, <= 64 filters, everything in
     // shared memory (16-frame tiles)
-    if (plan->tc && plan->variant == 5 && N == 512 && d->preemph == 0.f && d->dither == 0.f && F <= 8 * kWMaxNT) {
+    if (plan->tc && plan->variant == 5 && N == 512 && d->preemph == 0.f && d->dither == 0.f && F <= 8 * kWMaxNT && !plan->bf16_bank) {
       const int w_span = (kWTile - 1) * S + L;
       const size_t w_bytes = WLayout::bytes(w_span, L, (int)(tc_frags.size() / 4));
       if (w_bytes <= smem_cap) {

@@ -814,6 +814,21 @@ __device__ __forceinline__ float4 ldg_keep(const float4* ptr) {
   return v;
 }
 
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// x0 (lower half) and x1 (upper half) as bf16, and the same for their rounding residuals
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& p1, uint32_t& p2) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(x1), "f"(x0));
+  const float r0 = x0 - __uint_as_float(p1 << 16);
+  const float r1 = x1 - __uint_as_float(p1 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(r1), "f"(r0));
+}
+
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -910,11 +925,73 @@ __device__ __forceinline__ void tc_issue(const StftParams& p, const int* __restr
   }
 }
 
+// One bank item on bf16 m16n8k16 MMAs: NM 16-frame halves (frames m_first + 16 m) x eight filters x `left`
+// sixteen-bin blocks.  A 16-bin block is ONE MMA k-step (k = 2t, 2t+1, 2t+8, 2t+9 <-> bins 4t .. 4t+3: the
+// same conflict-free loads as the tf32 path); spectra and weights are split into two bf16 terms each and
+// the products p1 w1, p2 w1, p1 w2 are accumulated: three MMAs per block instead of six, weight fragments
+// half the size; relative error <= 3 * 2^-17 on sums of non-negative terms (measured 7e-6; tolerance 1e-4).
+template <int NM, int TS>
+__device__ __forceinline__ void bank_item_bf16(const float* __restrict__ pa, const float4* __restrict__ fr, int left,
+                                               float* __restrict__ out, int m_first, int n0, int g, int t, int nframes,
+                                               const StftParams& p, bool use_log, float log_floor) {
+  float acc[NM][2][4];  // [half][main | correction][fragment]
+#pragma unroll
+  for (int m = 0; m < NM; ++m)
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[m][q][i] = 0.f;
+#pragma unroll 2
+  do {
+    const float4 f = ldg_keep(fr);
+    const uint32_t w1b0 = __float_as_uint(f.x), w1b1 = __float_as_uint(f.y);
+    const uint32_t w2b0 = __float_as_uint(f.z), w2b1 = __float_as_uint(f.w);
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      const float* __restrict__ pm = pa + 16 * m;
+      uint32_t p1[4], p2[4];
+      split_bf16x2(pm[0], pm[TS], p1[0], p2[0]);                   // row g,     bins 4t, 4t+1
+      split_bf16x2(pm[8], pm[TS + 8], p1[1], p2[1]);               // row g + 8
+      split_bf16x2(pm[2 * TS], pm[3 * TS], p1[2], p2[2]);          // row g,     bins 4t+2, 4t+3
+      split_bf16x2(pm[2 * TS + 8], pm[3 * TS + 8], p1[3], p2[3]);  // row g + 8
+      mma_bf16(acc[m][0], p1[0], p1[1], p1[2], p1[3], w1b0, w1b1);
+      mma_bf16(acc[m][1], p2[0], p2[1], p2[2], p2[3], w1b0, w1b1);
+      mma_bf16(acc[m][1], p1[0], p1[1], p1[2], p1[3], w2b0, w2b1);
+    }
+    pa += 16 * TS;
+    fr += 32;
+  } while (--left > 0);
+  const int C = p.C;
+  const bool c0 = n0 + 2 * t < p.F, c1 = n0 + 2 * t + 1 < p.F;
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = acc[m][1][i] + acc[m][0][i];
+      if (use_log) v[i] = fast_log(fmaxf(v[i], log_floor));
+    }
+    const int row = m_first + 16 * m;
+    float* __restrict__ r0 = out + row * C;
+    float* __restrict__ r1 = r0 + 8 * C;
+    if (row + g < nframes) {
+      if (c0) __stcs(r0, v[0]);
+      if (c1) __stcs(r0 + 1, v[1]);
+    }
+    if (row + g + 8 < nframes) {
+      if (c0) __stcs(r1, v[2]);
+      if (c1) __stcs(r1 + 1, v[3]);
+    }
+  }
+}
+
 // An item with this m0 covers BOTH 16-frame halves of a 32-frame tile: one fetch of a weight
 // fragment feeds two A tiles.  Used when there are at least as many filter groups as warps (dense
 // banks: gammatone-64 has 8 groups x 17 blocks = 136 KB of fragments, far beyond the L1; with one
 // item per (group, half) every tile pulled them through the L2 twice: 8.5 KB per frame).
 constexpr int kBothHalves = 0x7fff;
+constexpr int kBothHalvesBf16 = 0x7ffe;  // the same with bf16 fragments (bank_item_bf16)
+constexpr int kHalfBf16 = 0x4000;        // flag on m0: one half, bf16 fragments
 
 template <int TS>
 __device__ __forceinline__ void bank_tc(int warp, int lane, const float* __restrict__ s_P,
@@ -933,6 +1010,18 @@ __device__ __forceinline__ void bank_tc(int warp, int lane, const float* __restr
   for (int it = s_wstart[warp]; it < it_end; ++it) {
     const int4 d = s_items[it];
     const int n0 = d.x & 0xffff, m0 = d.x >> 16;
+    if (m0 == kBothHalvesBf16) {
+      bank_item_bf16<2, TS>(s_P + d.y * (16 * TS) + lane_p, frags + d.w + lane, d.z, out_tile + n0 + lane_o, 0, n0, g, t,
+                            nframes, p, use_log, log_floor);
+      continue;
+    }
+    if (m0 & kHalfBf16) {
+      const int mh = m0 & ~kHalfBf16;
+      if (mh >= nframes) continue;
+      bank_item_bf16<1, TS>(s_P + d.y * (16 * TS) + mh + lane_p, frags + d.w + lane, d.z, out_tile + n0 + lane_o, mh, n0,
+                            g, t, nframes, p, use_log, log_floor);
+      continue;
+    }
     if (m0 == kBothHalves) {
       const float* __restrict__ pa = s_P + d.y * (16 * TS) + lane_p;
       const float4* __restrict__ fr = frags + d.w + lane;
