@@ -380,11 +380,12 @@ class Deltas(PostProcessor):
         ``materialize()`` gives the plain tensor."""
         return LazyDeltas(self, feats, row_off)
 
-    def apply_device(self, feats, row_off=None):
+    def apply_device(self, feats, row_off=None, out=None):
         """``(rows, C)`` float32 CUDA tensor -> ``(rows, C * (num_deltas + 1))``
 
         `row_off` (int64 CUDA tensor, ``n_utts + 1``) delimits utterances packed along the rows;
-        the filter never reaches across a boundary.  Default: one utterance.
+        the filter never reaches across a boundary.  Default: one utterance.  `out`: a contiguous
+        float32 CUDA tensor of the result's shape to write into instead of a new one.
         """
         import ctypes
 
@@ -397,7 +398,11 @@ class Deltas(PostProcessor):
         feats = feats.contiguous()
         if row_off is None:
             row_off = torch.tensor([0, rows], dtype=torch.int64, device=feats.device)
-        out = torch.empty((rows, cols * (self.num_deltas + 1)), dtype=torch.float32, device=feats.device)
+        shape = (rows, cols * (self.num_deltas + 1))
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=feats.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous float32 tensor of shape {shape}")
         taps = np.concatenate(self._filts[1:] + [np.zeros(0)]).astype(np.float32)
         lens = np.array([len(f) for f in self._filts[1:]], dtype=np.int32)
         with torch.cuda.device(feats.device):
