@@ -12,6 +12,7 @@
 // is fused: |y|^p never leaves registers; partial window sums go to shared-memory accumulators.
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdlib>
 #include <new>
 #include <vector>
@@ -42,6 +43,10 @@ struct SiParams {
   int valid_per_fft;       // exact outputs of one 1024-point block: 1024 - (M - 1)
   int ffts_per_tile;       // blocks that cover the (tile_frames + 1) * S pooled samples of a full tile
   int tile_frames;         // frames per tile on this path
+  // long supports (si_fft_big_kernel): blocks of 1024 * big_R points, one block per tile
+  const float2* hc_big;    // [C][R][1024] conj(DFT_N(h_c)) / N, element k = R * n1 + n2 at [n2][n1]
+  const float2* tw_big;    // [R][1024]    W_N^(n2 * k1) at [n2][k1]
+  int big_R;
 };
 
 // y index i of the full convolution reads padded samples i-k; padded index q maps to x[q - pad_left].
@@ -349,6 +354,179 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// overlap-save for long supports (M - 1 + 2 S beyond what three 1024-point blocks cover, e.g. the
+// triangular mel bank: 6 987 taps): blocks of N = 1024 R points, R = 2 ... 16, transformed by
+// the whole CTA in four steps (n = R n1 + n2, k = k1 + 1024 k2):
+//   rows    : warp n2 runs the in-register 1024-point FFT over n1, multiplies by W_N^(n2 k1) and
+//             writes row n2 of the 16 x 1024 work buffer Z (which is also its exchange scratch);
+//   columns : a thread takes column k1, runs the R-point DFT over n2 and owns outputs k1 + 1024 k2.
+// One block per tile: V = N - (M - 1) exact outputs hold V / S - 1 whole frames (both pooling
+// halves), so a frame is ONE dot product of the 2 S window with |y|^p -- no partial sums.
+// The spectrum of the (real) samples is kept as its lower half, stored by residue k mod R so
+// that the rows of the inverse transform read it contiguously; the upper half is the mirrored
+// conjugate.  16 / R filters are transformed at a time (16 warps = 16 rows).  The order of all
+// sums is fixed, results are bitwise reproducible.
+// ------------------------------------------------------------------------------------------
+constexpr int kSiBigRowStride = 520;  // complex entries per residue row of the half spectrum (513 used)
+
+struct SiBigSmem {
+  int z, xh, tw, w, total;  // float offsets; total in bytes
+};
+__host__ __device__ inline SiBigSmem si_big_layout(int S, int R) {
+  SiBigSmem l;
+  int o = 0;
+  auto take = [&](int n) { const int at = o; o += (n + 3) & ~3; return at; };
+  l.z = take(2 * kSiFftWarps * kSiFftN);
+  l.xh = take(2 * R * kSiBigRowStride);
+  l.tw = take(2 * kSiFftN);
+  l.w = take(2 * S);
+  l.total = o * 4;
+  return l;
+}
+
+// 1024-point forward FFT of z (element index = lane + 32 * register, in and out); `row` (1024
+// complex values of shared memory owned by this warp) is the exchange scratch, XOR-swizzled so
+// that both the row-wise stores and the column-wise loads are conflict free without padding
+__device__ __forceinline__ void si_fft1024_row(cplx (&z)[32], int lane, const float2* __restrict__ s_tw,
+                                               cplx* __restrict__ row) {
+  Dft<32>::run(z);
+#pragma unroll
+  for (int k1 = 1; k1 < 32; ++k1) z[k1] = cmul(z[k1], s_tw[k1 * 32 + lane]);
+  __syncwarp();
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) row[lane * 32 + (k1 ^ lane)] = z[k1];
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) z[n2] = row[n2 * 32 + (lane ^ n2)];
+  __syncwarp();
+  Dft<32>::run(z);
+}
+
+template <bool POWER, int R>
+__global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_big_kernel(const __grid_constant__ SiParams p) {
+  constexpr int N = kSiFftN * R, SLOTS = kSiFftWarps / R;
+  extern __shared__ __align__(16) float smem[];
+  const int S = p.S, M = p.M, C = p.C;
+  const SiBigSmem lay = si_big_layout(S, R);
+  cplx* s_z = reinterpret_cast<cplx*>(smem + lay.z);
+  float* s_zf = smem + lay.z;
+  cplx* s_xh = reinterpret_cast<cplx*>(smem + lay.xh);
+  float2* s_tw = reinterpret_cast<float2*>(smem + lay.tw);
+  float* s_w = smem + lay.w;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = warp / R, n2 = warp % R;
+  cplx* row = s_z + warp * kSiFftN;
+
+  for (int i = tid; i < 2 * S; i += kSiFftThreads) s_w[i] = p.window[i];
+  for (int i = tid; i < kSiFftN; i += kSiFftThreads) s_tw[i] = p.tw[i];
+
+  for (long long tile_idx = blockIdx.x; tile_idx < p.n_tiles; tile_idx += gridDim.x) {
+    const pds_tile tile = p.tiles[tile_idx];
+    const int nframes = tile.nframes;
+    __syncthreads();
+    // ---- spectrum of the block: rows by warps 0 .. R-1 ------------------------------------
+    if (warp < R) {
+      // block sample j = R n1 + warp is padded sample tile.start - (M - 1) + j
+      const long long g0 = (long long)tile.start - (M - 1) - p.pad_left + warp;
+      const float* __restrict__ sig = p.sig + tile.sig_off;
+      cplx z[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const long long g = g0 + (long long)R * (lane + 32 * r);
+        z[r] = cmake((g >= 0 && g < tile.sig_len) ? __ldg(sig + g) : 0.f, 0.f);
+      }
+      si_fft1024_row(z, lane, s_tw, row);
+      if (warp > 0) {
+        const float2* __restrict__ tw = p.tw_big + warp * kSiFftN + lane;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) z[r] = cmul(z[r], __ldg(tw + 32 * r));
+      }
+#pragma unroll
+      for (int r = 0; r < 32; ++r) row[lane + 32 * r] = z[r];
+    }
+    __syncthreads();
+    for (int col = tid; col < kSiFftN; col += kSiFftThreads) {
+      cplx v[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) v[q] = s_z[q * kSiFftN + col];
+      Dft<R>::run(v);
+      // keep conj(X[k]) for k = col + 1024 k2 <= N / 2 at [k mod R][k div R]
+      cplx* __restrict__ dst = s_xh + (col % R) * kSiBigRowStride + col / R;
+#pragma unroll
+      for (int k2 = 0; k2 <= R / 2; ++k2)
+        if (k2 < R / 2 || col == 0) dst[k2 * (kSiFftN / R)] = cmake(cre(v[k2]), -cim(v[k2]));
+    }
+    __syncthreads();
+
+    // ---- 16 / R filters at a time -----------------------------------------------------------
+    for (int c0 = 0; c0 < C; c0 += SLOTS) {
+      const int c = c0 + slot;
+      if (c < C) {
+        const float2* __restrict__ hc = p.hc_big + ((size_t)c * R + n2) * kSiFftN + lane;
+        const cplx* __restrict__ lo = s_xh + n2 * kSiBigRowStride + lane;
+        // k = R n1 + n2 > N / 2 is the conjugate of entry N - k: residue (R - n2) mod R, index
+        // 1023 - n1 (1024 - n1 for residue 0)
+        const cplx* __restrict__ hi = s_xh + ((R - n2) % R) * kSiBigRowStride + (1023 + (n2 == 0)) - lane;
+        cplx z[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          cplx x;
+          if (r < 16) {
+            x = lo[32 * r];
+          } else {
+            const cplx m = hi[-32 * r];
+            x = cmake(cre(m), -cim(m));
+          }
+          z[r] = cmul(x, __ldg(hc + 32 * r));
+        }
+        si_fft1024_row(z, lane, s_tw, row);
+        if (n2 > 0) {
+          const float2* __restrict__ tw = p.tw_big + n2 * kSiFftN + lane;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) z[r] = cmul(z[r], __ldg(tw + 32 * r));
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r) row[lane + 32 * r] = z[r];
+      }
+      __syncthreads();
+      // columns: |y|^p of output k1 + 1024 k2 of slot s replaces the real part of Z[s][k2][k1]
+      for (int q = tid; q < SLOTS * kSiFftN; q += kSiFftThreads) {
+        const int s = q / kSiFftN, col = q - s * kSiFftN;
+        if (c0 + s < C) {
+          cplx* __restrict__ zc = s_z + s * N + col;
+          cplx v[R];
+#pragma unroll
+          for (int k = 0; k < R; ++k) v[k] = zc[k * kSiFftN];
+          Dft<R>::run(v);
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            float u = cnorm(v[k]);
+            if (!POWER) u = approx_sqrt(u);
+            reinterpret_cast<float*>(zc + k * kSiFftN)[0] = u;
+          }
+        }
+      }
+      __syncthreads();
+      // pooling: frame t of slot s = window . |y|^p[(M - 1) + t S ... + 2 S)
+      for (int task = warp; task < SLOTS * nframes; task += kSiFftWarps) {
+        const int s = task / nframes, t = task - s * nframes;
+        if (c0 + s >= C) continue;
+        const float* __restrict__ u = s_zf + 2 * (s * N + (M - 1) + t * S);
+        float acc = 0.f;
+        for (int n = lane; n < 2 * S; n += 32) acc = fmaf(s_w[n], u[2 * n], acc);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) {
+          if (p.use_log) acc = __logf(fmaxf(acc, p.log_floor));
+          p.out[(tile.out_row + t) * C + c0 + s] = acc;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace pds
 
 using namespace pds;
@@ -363,12 +541,48 @@ struct pds_si_plan {
   bool fft = false;  // overlap-save kernel usable
   size_t fft_smem_bytes = 0;
   int fft_grid_limit = 0;
+  int big_R = 0;  // > 0: si_fft_big_kernel with blocks of 1024 * big_R points
+  size_t big_smem_bytes = 0;
   SiParams params{};
   void* d_blob = nullptr;
 };
 
 namespace {
+// in-place radix-2 FFT in double precision (filter spectra of the long-support path)
+void host_fft(std::vector<std::complex<double>>& a) {
+  const size_t n = a.size();
+  for (size_t i = 1, j = 0; i < n; ++i) {
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(a[i], a[j]);
+  }
+  const double two_pi = 6.283185307179586476925286766559;
+  for (size_t len = 2; len <= n; len <<= 1) {
+    std::vector<std::complex<double>> w(len / 2);
+    for (size_t k = 0; k < len / 2; ++k) w[k] = std::polar(1.0, -two_pi * (double)k / (double)len);
+    for (size_t i = 0; i < n; i += len)
+      for (size_t k = 0; k < len / 2; ++k) {
+        const std::complex<double> u = a[i + k], v = a[i + k + len / 2] * w[k];
+        a[i + k] = u + v;
+        a[i + k + len / 2] = u - v;
+      }
+  }
+}
+
 using SiKernel = void (*)(const SiParams);
+const void* pick_si_big(const pds_si_plan* plan) {
+  switch (plan->big_R * 2 + (plan->power ? 1 : 0)) {
+    case 4: return reinterpret_cast<const void*>(si_fft_big_kernel<false, 2>);
+    case 5: return reinterpret_cast<const void*>(si_fft_big_kernel<true, 2>);
+    case 8: return reinterpret_cast<const void*>(si_fft_big_kernel<false, 4>);
+    case 9: return reinterpret_cast<const void*>(si_fft_big_kernel<true, 4>);
+    case 16: return reinterpret_cast<const void*>(si_fft_big_kernel<false, 8>);
+    case 17: return reinterpret_cast<const void*>(si_fft_big_kernel<true, 8>);
+    case 32: return reinterpret_cast<const void*>(si_fft_big_kernel<false, 16>);
+    default: return reinterpret_cast<const void*>(si_fft_big_kernel<true, 16>);
+  }
+}
 SiKernel pick_si(const pds_si_plan* plan) {
   if (plan->real) return plan->power ? si_direct_kernel<true, true> : si_direct_kernel<true, false>;
   return plan->power ? si_direct_kernel<false, true> : si_direct_kernel<false, false>;
@@ -404,10 +618,53 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
       valid_per_fft > 0 ? std::min(kSiFftMaxTileFrames, (kSiFftBlocks * valid_per_fft) / plan->S - 1) : 0;
   const char* force = getenv("PDS_SI_KERNEL");
   plan->fft = fft_tile_frames >= 1 && !(force && force[0] == 'd');
+  // long supports: the smallest block of 1024 R points (R = 2 ... 16) of which at least 40 % are
+  // exact outputs (R = 16 whenever it still holds two hops); preferred over the 1024-point
+  // kernel once that one keeps less than 40 % of its outputs
+  {
+    const bool want_big = !(force && force[0] == 'd') && !(force && force[0] == 's') &&
+                          (fft_tile_frames < 1 || valid_per_fft * 5 < kSiFftN * 2 || (force && force[0] == 'b'));
+    for (int R = 2; want_big && R <= 16 && plan->big_R == 0; R *= 2) {
+      const long long V = (long long)kSiFftN * R - (plan->M - 1);
+      if (V >= 2 * plan->S && (V * 5 >= (long long)kSiFftN * R * 2 || R == 16)) plan->big_R = R;
+    }
+    if (plan->big_R) plan->fft = false;
+  }
+  const int big_N = kSiFftN * plan->big_R;
   const size_t o_hc = (o_w + 2 * (size_t)plan->S * sizeof(float) + 15) & ~(size_t)15;
   const size_t o_tw = o_hc + (plan->fft ? (size_t)plan->C * kSiFftN * sizeof(float2) : 0);
-  const size_t bytes = o_tw + (plan->fft ? (size_t)kSiFftN * sizeof(float2) : 0);
+  const size_t o_hcb = o_tw + ((plan->fft || plan->big_R) ? (size_t)kSiFftN * sizeof(float2) : 0);
+  const size_t o_twb = o_hcb + (size_t)plan->C * big_N * sizeof(float2);
+  const size_t bytes = o_twb + (size_t)big_N * sizeof(float2);
   std::vector<unsigned char> blob(bytes, 0);
+  if (plan->big_R) {
+    const int R = plan->big_R;
+    const double two_pi = 6.283185307179586476925286766559;
+    float2* hcb = reinterpret_cast<float2*>(blob.data() + o_hcb);
+    std::vector<std::complex<double>> h(big_N);
+    for (int c = 0; c < plan->C; ++c) {
+      std::fill(h.begin(), h.end(), std::complex<double>(0.0, 0.0));
+      for (int m = 0; m < plan->M; ++m)
+        h[m] = std::complex<double>(d->h_real[(size_t)c * plan->M + m],
+                                    plan->real ? 0.0 : d->h_imag[(size_t)c * plan->M + m]);
+      host_fft(h);
+      for (int k = 0; k < big_N; ++k)  // conj(H[k]) / N at [k mod R][k div R]
+        hcb[((size_t)c * R + k % R) * kSiFftN + k / R] =
+            make_float2((float)(h[k].real() / big_N), (float)(-h[k].imag() / big_N));
+    }
+    float2* twb = reinterpret_cast<float2*>(blob.data() + o_twb);
+    for (int n2 = 0; n2 < R; ++n2)
+      for (int k1 = 0; k1 < kSiFftN; ++k1) {
+        const double a = two_pi * (double)(((long long)n2 * k1) % big_N) / big_N;
+        twb[n2 * kSiFftN + k1] = make_float2((float)std::cos(a), (float)(-std::sin(a)));
+      }
+    float2* tw = reinterpret_cast<float2*>(blob.data() + o_tw);
+    for (int k1 = 0; k1 < 32; ++k1)
+      for (int l = 0; l < 32; ++l) {
+        const double a = two_pi * ((l * k1) % kSiFftN) / kSiFftN;
+        tw[k1 * 32 + l] = make_float2((float)std::cos(a), (float)(-std::sin(a)));
+      }
+  }
   if (plan->fft) {
     const double two_pi = 6.283185307179586476925286766559;
     std::vector<double> cs(kSiFftN), sn(kSiFftN);
@@ -456,6 +713,14 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
   p.valid_per_fft = valid_per_fft;
   p.tile_frames = plan->fft ? fft_tile_frames : kSiTileFrames;
   p.ffts_per_tile = plan->fft ? ((fft_tile_frames + 1) * plan->S + valid_per_fft - 1) / valid_per_fft : 0;
+  p.hc_big = reinterpret_cast<const float2*>(base + o_hcb);
+  p.tw_big = reinterpret_cast<const float2*>(base + o_twb);
+  p.big_R = plan->big_R;
+  if (plan->big_R) {
+    p.valid_per_fft = big_N - (plan->M - 1);
+    p.tile_frames = p.valid_per_fft / plan->S - 1;
+    p.ffts_per_tile = 1;
+  }
   const int S = plan->S, M = plan->M, C = plan->C;
   const int Mp = (M + 7) & ~7;
   const int ny_max = (kSiTileFrames + 1) * S;
@@ -466,6 +731,22 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
                      sizeof(float2) * (size_t)Mp * (kSiThreads / 32);
   cudaDeviceProp prop;
   err = cudaGetDeviceProperties(&prop, device);
+  if (err == cudaSuccess && plan->big_R) {
+    plan->big_smem_bytes = si_big_layout(S, plan->big_R).total;
+    if (plan->big_smem_bytes <= prop.sharedMemPerBlockOptin &&
+        cudaFuncSetAttribute(pick_si_big(plan), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)plan->big_smem_bytes) == cudaSuccess) {
+      plan->fft_grid_limit = prop.multiProcessorCount;
+      plan->tile_frames = p.tile_frames;
+      *out = plan;
+      return PDS_OK;
+    }
+    cudaGetLastError();
+    set_error("SI geometry (S=%d, max_support=%d) needs %zu bytes of shared memory for the long-support kernel", S,
+              M, plan->big_smem_bytes);
+    pds_si_plan_destroy(plan);
+    return PDS_ERR_UNSUPPORTED;
+  }
   if (err != cudaSuccess || plan->smem_bytes > prop.sharedMemPerBlockOptin) {
     set_error("SI geometry (S=%d, max_support=%d, %d filters) needs %zu bytes of shared memory", S,
               M, C, plan->smem_bytes);
@@ -564,6 +845,13 @@ extern "C" int pds_si_run(pds_si_plan* plan, const float* d_signal, const pds_ti
   PDS_REQUIRE(d_signal && d_tiles && d_out && n_tiles > 0, "null buffer");
   SiParams p = plan->params;
   p.sig = d_signal, p.tiles = d_tiles, p.n_tiles = n_tiles, p.out = d_out;
+  if (plan->big_R) {
+    const int grid = (int)std::min<int64_t>(n_tiles, plan->fft_grid_limit);
+    void* args[] = {&p};
+    PDS_CUDA_CHECK(cudaLaunchKernel(pick_si_big(plan), dim3(grid), dim3(kSiFftThreads), args, plan->big_smem_bytes,
+                                    static_cast<cudaStream_t>(stream)));
+    return PDS_OK;
+  }
   if (plan->fft) {
     const int grid = (int)std::min<int64_t>(n_tiles, plan->fft_grid_limit);
     if (plan->power)

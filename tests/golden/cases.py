@@ -153,6 +153,27 @@ SI_CASES = {
     ),
 }
 
+# supports beyond one 1024-point block (``si_long.npz``): the kernels with 1024 * R-point blocks
+SI_LONG_CASES = {
+    "si_fbank40": ({"name": "si", "bank": "fbank"}, ("randn", 21, 20000)),  # 6 987 taps, real filters, R = 16
+    "si_gabor128_power": (  # 838 taps, R = 2
+        {"name": "si", "bank": {"name": "gabor", "scaling_function": "mel", "num_filts": 128}, "use_power": True},
+        ("randn", 22, 9000),
+    ),
+    "si_fbank8_energy": (  # 2 206 taps, R = 4, energy column (a pure delay as the first filter)
+        {"name": "si", "bank": {"name": "fbank", "num_filts": 8}, "include_energy": True},
+        ("randn", 23, 12000),
+    ),
+    "si_fbank16_power_nolog": (  # 3 671 taps, R = 8
+        {"name": "si", "bank": {"name": "fbank", "num_filts": 16}, "use_power": True, "use_log": False},
+        ("randn", 24, 15000),
+    ),
+    "si_gammatone100_causal": (  # 934 taps, causal pooling window, complex filters, R = 2
+        {"name": "si", "bank": {"name": "gammatone", "scaling_function": "mel", "num_filts": 100}},
+        ("randn", 25, 7000),
+    ),
+}
+
 BANK_CASES = {  # table-level goldens: supports, truncated / frequency / impulse responses
     "fbank40": ({"name": "fbank"}, 512),
     "fbank24_8k": ({"name": "fbank", "num_filts": 24, "sampling_rate": 8000, "high_hz": 3800}, 256),

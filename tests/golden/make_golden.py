@@ -4,8 +4,8 @@ Run in the build container (the reference is importable there, not on the GPU bo
 
     python tests/golden/make_golden.py
 
-Outputs (committed): ``stft.npz``, ``si.npz``, ``banks.npz``, ``post.npz``, ``kaldi.npz``, ``extra.npz``
-(``python tests/golden/make_golden.py extra`` rebuilds the last one alone).
+Outputs (committed): ``stft.npz``, ``si.npz``, ``banks.npz``, ``post.npz``, ``kaldi.npz``, ``extra.npz``,
+``si_long.npz`` (``python tests/golden/make_golden.py extra`` / ``si_long`` rebuild the last two alone).
 The reference's numpy path is used (``config.USE_FFTPACK = False``); its scipy.fftpack branch
 is pinned to it by the reference's own tests.  Nothing here is imported at test time except
 ``cases.py``.
@@ -194,9 +194,29 @@ def extra_goldens():
     np.savez_compressed(os.path.join(HERE, "extra.npz"), **out)
 
 
+def si_long_goldens():
+    """``si_long.npz``: short-integration features of banks whose impulse responses are longer than
+    one 1024-point block (the signals are regenerated from their seeds at test time)"""
+    out = {}
+    for name, (cfg, spec) in cases.SI_LONG_CASES.items():
+        signal = make_signal(spec).astype(np.float32).astype(np.float64)
+        computer = build(compute.FrameComputer, cfg)
+        out[name + "/feats"] = computer.compute_full(signal).astype(np.float32)
+        lin = build(compute.FrameComputer, dict(cfg, use_log=False))
+        out[name + "/feats_linear"] = lin.compute_full(signal)
+        out[name + "/geometry"] = np.array(
+            [computer.frame_shift, computer._max_support, computer._translation,
+             computer._frame_length, computer._dft_size, int(computer.frame_style == "centered")]
+        )
+    np.savez_compressed(os.path.join(HERE, "si_long.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "extra":
         extra_goldens()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "si_long":
+        si_long_goldens()
         sys.exit(0)
     stft_goldens()
     si_goldens()
@@ -204,6 +224,7 @@ if __name__ == "__main__":
     post_goldens()
     kaldi_goldens()
     extra_goldens()
+    si_long_goldens()
     for name in sorted(os.listdir(HERE)):
         if name.endswith(".npz"):
             print(name, os.path.getsize(os.path.join(HERE, name)))

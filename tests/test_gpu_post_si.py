@@ -253,3 +253,52 @@ def test_config4_sixty_second_utterance(speech, golden):
     got = si.compute_full(signal)
     assert got.shape == want.shape == (6000, 41)
     assert np.abs(got - want).max() <= 1e-3
+
+
+# ---- short integration with supports longer than one 1024-point block ---------------------------
+def _seeded(spec):
+    _, seed, length = spec
+    return (np.random.default_rng(seed).standard_normal(length) * 1000.0).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", sorted(cases.SI_LONG_CASES))
+def test_si_long_supports_match_reference(speech, golden, name):
+    """the 1024 * R-point overlap-save kernel (R = 2 ... 16) against the reference's own output
+    (tests/golden/make_golden.py si_long): 838 ... 6 987 taps, real and complex filters, centered and
+    causal pooling"""
+    cfg, spec = cases.SI_LONG_CASES[name]
+    data = golden("si_long")
+    signal = _seeded(spec)
+    computer = build(speech, speech.compute.FrameComputer, cfg)
+    assert computer._max_support == int(data[name + "/geometry"][1])
+    got = computer.compute_full(signal)
+    want = data[name + "/feats"]
+    assert got.shape == want.shape
+    lin = build(speech, speech.compute.FrameComputer, dict(cfg, use_log=False))
+    lin_got, lin_want = lin.compute_full(signal).astype(np.float64), data[name + "/feats_linear"]
+    if cfg.get("use_log", True):
+        assert np.abs(got - want).max() <= 1e-3
+    scale = np.maximum(np.abs(lin_want), 1e-6 * np.abs(lin_want).max(axis=1, keepdims=True))
+    worst = (np.abs(lin_got - lin_want) / scale).max()
+    print(f"WORST {name}: linear relative error {worst:.3g}")
+    assert worst <= 1e-4
+    # batches, ragged lengths and the chunked interface go through the same tiles
+    pieces = [signal[:n] for n in (0, 1, 700, 5000, len(signal))]
+    for piece, feats in zip(pieces, computer.compute_batch(pieces)):
+        assert np.array_equal(feats, computer.compute_full(piece))
+    chunked = speech.compute.frame_by_frame_calculation(computer, signal[:6000], chunk_size=1111)
+    assert np.allclose(chunked, computer.compute_full(signal[:6000]), atol=2e-5 if cfg.get("use_log", True) else 0, rtol=2e-5)
+
+
+@pytest.mark.parametrize("name", sorted(cases.SI_CASES))
+def test_si_long_kernel_on_short_supports(speech, golden, monkeypatch, name):
+    """PDS_SI_KERNEL=big forces the long-support kernel onto the standard cases (R = 2)"""
+    monkeypatch.setenv("PDS_SI_KERNEL", "big")
+    cfg, _ = cases.SI_CASES[name]
+    data = golden("si")
+    computer = build(speech, speech.compute.FrameComputer, cfg)
+    signal = data[name + "/signal"]
+    want = data[name + "/feats"]
+    got = computer.compute_full(signal)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= (1e-3 if cfg.get("use_log", True) else 1e-4 * np.abs(want).max())

@@ -131,3 +131,22 @@ def test_stft_oracle_config1_full_wav(golden, speech):
         data["c1/signal"].astype(np.float64), computer._window, computer._dft_size, computer._filt_start_idxs,
         computer._truncated_filts, computer.frame_shift, computer.pad_left, True, True, True, True, linear=True)
     assert np.allclose(lin, data["c1/feats_linear"], rtol=1e-11, atol=0)
+
+
+@pytest.mark.parametrize("name", ["si_fbank8_energy", "si_gammatone100_causal", "si_fbank16_power_nolog"])
+def test_si_oracle_long_supports(speech, golden, name):
+    """impulse responses longer than 1024 samples: the oracle on the HOST tables of the package (built
+    without a GPU) against the reference's output (make_golden.py si_long)"""
+    cfg, (_, seed, length) = cases.SI_LONG_CASES[name]
+    data = golden("si_long")
+    signal = (np.random.default_rng(seed).standard_normal(length) * 1000.0).astype(np.float32)
+    computer = speech.alias_factory_subclass_from_arg(speech.compute.FrameComputer, cfg)
+    S, max_support, translation, _, _, centered = (int(v) for v in data[name + "/geometry"])
+    assert (computer.frame_shift, computer._max_support, computer._translation) == (S, max_support, translation)
+    got = oracle.si_features(
+        signal, computer._impulse_responses, computer._window.reshape(-1), S, computer._zero_pad,
+        computer._pool_start, computer._frames_lost, cfg.get("use_power", False), cfg.get("use_log", True),
+    )
+    want = data[name + "/feats"]
+    assert got.shape == want.shape
+    assert np.allclose(got, want, rtol=2e-6, atol=2e-6)  # the golden is stored as float32
