@@ -1,7 +1,10 @@
 // stft.cu -- host side of the fused STFT frame-feature path: plan construction (constant tables,
 // kernel choice), tile tables, launches, and the C ABI.  The kernels live in stft_device.cuh and are
 // instantiated by the stft_k_*.cu translation units.
+#include <cuda_fp16.h>
+
 #include "stft_device.cuh"
+#include "stft_umma.cuh"
 
 // ==========================================================================================
 // host side
@@ -25,6 +28,9 @@ struct pds_stft_plan {
   size_t blue_smem_bytes = 0;
   int blue_grid_limit = 0;
   bool bf16_bank = false;  // dense bank contracted with bf16 two-term splits (fragment layout differs)
+  bool um = false;  // stft_umma_kernel: the transform on tcgen05 (dft_size 512, frame shift a multiple of 4, <= 64 filters)
+  size_t um_smem_bytes = 0;
+  int um_nt = 0;
   bool w = false;  // stft_w_kernel usable (float32 input; 16-frame tiles)
   size_t w_smem_bytes = 0;
   int w_nt = 0;
@@ -140,6 +146,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     if (force[0] == '1' || force[0] == 'w' || force[0] == 's') plan->variant = 1;
     if (force[0] == '2') plan->variant = 2;
     if (force[0] == 'p') plan->variant = 5;
+    if (force[0] == 'u') plan->variant = 6;
     if (force[0] == 'x') plan->variant = 3;
     if (force[0] == 'y') plan->variant = 4;
   }
@@ -354,6 +361,19 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
         p.span_max = w_span;
       }
     }
+    // tcgen05 transform: dft_size 512, frame shift a multiple of four samples (16-byte frame starts), at most
+    // 64 filters, operands + two sample stages in shared memory
+    if (plan->tc && plan->variant == 6 && N == 512 && S % 4 == 0 && F <= 64) {
+      const int kch = 2 * ((L + 63) / 64);
+      const int nt = F <= 24 ? 3 : (F <= 40 ? 5 : 8);
+      const size_t um_bytes = (size_t)um_layout(kch, p.span_max, L, nt).total;
+      if (kch <= kUmMaxKch && um_bytes <= smem_cap) {
+        plan->um = true;
+        plan->um_smem_bytes = um_bytes;
+        plan->um_nt = nt;
+        p.um_kch = kch;
+      }
+    }
     if (!plan->fused && !plan->tc) plan->fast = false;  // huge frame shift / dft_size 2048: direct kernel
     if (plan->fast && plan->fused && d->preemph == 0.f && d->dither == 0.f) {
       const WsLayout ws = ws_layout(N, G, R1, p.span_max, p_rows, npairs, plan->C, pair_total);
@@ -452,6 +472,85 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   }
 
   // ---- one device blob -----------------------------------------------------------------
+  // stft_umma_kernel: constant operand, window, bank fragments in the kernel's bin order (see stft_umma.cuh)
+  std::vector<unsigned char> um_amat;
+  std::vector<float> um_window;
+  std::vector<uint32_t> um_frags;
+  std::vector<int> um_masks(4 * kUmSteps, 0), um_offs(4 * kUmSteps, 0);
+  if (plan->um) {
+    const int kch = p.um_kch;
+    um_window.assign(N, 0.f);
+    for (int i = 0; i < L; ++i) um_window[i] = d->window[i];
+    // row (TMEM lane) 32 q + 16 h + 8 im + g <-> k1 = 16 q + 8 h + g; row 8 holds Re Y[64] in place of Im Y[0].
+    // column position 8 c + k <-> j = 8 c + ((k + c) mod 8): the order in which lane c of a builder reads its samples
+    um_amat.assign(2 * (size_t)kch * kUmLboA, 0);
+    for (int row = 0; row < 128; ++row) {
+      const int qq = row / 32, hh = (row / 16) % 2, im = (row / 8) % 2, gg = row % 8;
+      const int k1 = 16 * qq + 8 * hh + gg;
+      for (int pos = 0; pos < 8 * kch; ++pos) {
+        const int c = pos / 8, k = pos % 8, j = 8 * c + ((k + c) & 7);
+        double v;
+        if (im && k1 == 0) v = (j % 2) ? -1.0 : 1.0;  // cos(pi j)
+        else {
+          const double a = two_pi * (double)((j * k1) % 128) / 128.0;
+          v = im ? -std::sin(a) : std::cos(a);
+        }
+        const __half hi = __float2half_rn((float)v);
+        const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+        const size_t at = (size_t)c * kUmLboA + (size_t)(row / 8) * 128 + (size_t)(row % 8) * 16 + (size_t)k * 2;
+        const unsigned short hb = __half_as_ushort(hi), lb = __half_as_ushort(lo);
+        std::memcpy(um_amat.data() + at, &hb, 2);
+        std::memcpy(um_amat.data() + (size_t)kch * kUmLboA + at, &lb, 2);
+      }
+    }
+    // bin of k-slot kk of step s in lane quarter q (-1: none)
+    auto bin_of = [](int qq, int s, int kk) {
+      const int k1 = 16 * qq + kk;
+      switch (s) {
+        case 0: return k1;
+        case 1: return 128 + k1;
+        case 2: return 256 - k1;
+        case 3: return k1 == 0 ? 64 : 128 - k1;   // the duplicate of bin 128 carries bin 64
+        default: return (qq == 0 && kk == 0) ? 192 : -1;
+      }
+    };
+    auto weight = [&](int f, int bin) -> float {
+      if (f >= F || bin < 0) return 0.f;
+      const int tt = bin - d->band_lo[f];
+      return (tt >= 0 && tt < d->band_len[f]) ? d->weights[d->band_off[f] + tt] : 0.f;
+    };
+    for (int qq = 0; qq < 4; ++qq)
+      for (int s = 0; s < kUmSteps; ++s) {
+        um_offs[qq * kUmSteps + s] = (int)(um_frags.size() / 128);
+        if (s == 4 && qq != 0) continue;
+        for (int nt = 0; nt < plan->um_nt; ++nt) {
+          bool any = false;
+          for (int kk = 0; kk < 16 && !any; ++kk)
+            for (int gg = 0; gg < 8 && !any; ++gg) any = weight(8 * nt + gg, bin_of(qq, s, kk)) != 0.f;
+          if (!any) continue;
+          um_masks[qq * kUmSteps + s] |= 1 << nt;
+          for (int ln = 0; ln < 32; ++ln) {
+            const int gg = ln / 4, tt = ln % 4;
+            uint32_t hi[4], lo[4];
+            const int kks[4] = {2 * tt, 2 * tt + 1, 2 * tt + 8, 2 * tt + 9};
+            for (int i = 0; i < 4; ++i) {
+              const float w = weight(8 * nt + gg, bin_of(qq, s, kks[i]));
+              hi[i] = bf16_rn(w);
+              uint32_t hb = hi[i] << 16;
+              float hf;
+              std::memcpy(&hf, &hb, 4);
+              lo[i] = bf16_rn(w - hf);
+            }
+            um_frags.push_back(hi[0] | (hi[1] << 16));
+            um_frags.push_back(hi[2] | (hi[3] << 16));
+            um_frags.push_back(lo[0] | (lo[1] << 16));
+            um_frags.push_back(lo[2] | (lo[3] << 16));
+          }
+        }
+      }
+  }
+  if (um_frags.empty()) um_frags.resize(4, 0u);
+
   auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
   size_t o_win = 0, o_tws = align16(o_win + sizeof(float) * N);
   size_t o_twp = align16(o_tws + sizeof(float2) * tw_stage.size());
@@ -468,7 +567,12 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   size_t o_baw = align16(o_tcf + sizeof(float) * tc_frags.size());
   size_t o_bb = align16(o_baw + sizeof(float2) * blue_aw.size());
   size_t o_btw = align16(o_bb + sizeof(float2) * blue_b.size());
-  size_t blob_bytes = align16(o_btw + sizeof(float2) * blue_tw.size());
+  size_t o_uma = align16(o_btw + sizeof(float2) * blue_tw.size());
+  size_t o_umw = align16(o_uma + um_amat.size());
+  size_t o_umf = align16(o_umw + sizeof(float) * um_window.size());
+  size_t o_umm = align16(o_umf + sizeof(uint32_t) * um_frags.size());
+  size_t o_umo = align16(o_umm + sizeof(int) * um_masks.size());
+  size_t blob_bytes = align16(o_umo + sizeof(int) * um_offs.size());
   std::vector<unsigned char> blob(blob_bytes, 0);
   std::memcpy(blob.data() + o_win, win.data(), sizeof(float) * N);
   if (!tw_stage.empty()) std::memcpy(blob.data() + o_tws, tw_stage.data(), sizeof(float2) * tw_stage.size());
@@ -488,6 +592,13 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     std::memcpy(blob.data() + o_bb, blue_b.data(), sizeof(float2) * blue_b.size());
     std::memcpy(blob.data() + o_btw, blue_tw.data(), sizeof(float2) * blue_tw.size());
   }
+  if (plan->um) {
+    std::memcpy(blob.data() + o_uma, um_amat.data(), um_amat.size());
+    std::memcpy(blob.data() + o_umw, um_window.data(), sizeof(float) * um_window.size());
+  }
+  std::memcpy(blob.data() + o_umf, um_frags.data(), sizeof(uint32_t) * um_frags.size());
+  std::memcpy(blob.data() + o_umm, um_masks.data(), sizeof(int) * um_masks.size());
+  std::memcpy(blob.data() + o_umo, um_offs.data(), sizeof(int) * um_offs.size());
   err = cudaMalloc(&plan->d_blob, blob_bytes);
   if (err == cudaSuccess) err = cudaMemcpy(plan->d_blob, blob.data(), blob_bytes, cudaMemcpyHostToDevice);
   if (err != cudaSuccess) {
@@ -512,6 +623,11 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   p.tc_items = reinterpret_cast<const int4*>(base + o_tci);
   p.tc_wstart = reinterpret_cast<const int*>(base + o_tcw);
   p.tc_frags = reinterpret_cast<const float4*>(base + o_tcf);
+  p.um_amat = base + o_uma;
+  p.um_window = reinterpret_cast<const float*>(base + o_umw);
+  p.um_frags = base + o_umf;
+  p.um_masks = reinterpret_cast<const int*>(base + o_umm);
+  p.um_offs = reinterpret_cast<const int*>(base + o_umo);
   p.tc_nitems = tc_nitems;
   p.w_frag4 = (int)(tc_frags.size() / 4);
   p.w_probe = getenv("PDS_W_PROBE") ? atoi(getenv("PDS_W_PROBE")) : 0;
@@ -548,6 +664,14 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
         cudaGetLastError();
         plan->tc = false;
       }
+    }
+  }
+  for (int dt = 0; dt < 2 && plan->um; ++dt) {
+    err = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_umma(plan->power, dt, plan->um_nt)),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->um_smem_bytes);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      plan->um = false;
     }
   }
   for (int dt = 0; dt < 2 && plan->blue; ++dt) {
@@ -615,6 +739,7 @@ extern "C" int pds_stft_is_fast_path(const pds_stft_plan* plan) { return plan &&
 extern "C" const char* pds_stft_kernel_name(const pds_stft_plan* plan, int sig_dtype) {
   if (!plan) return "";
   if (plan->ws && sig_dtype == PDS_F32 && plan->want_ws) return "pds::stft_ws_kernel";
+  if (plan->um) return "pds::stft_umma_kernel";
   if (plan->w && sig_dtype == PDS_F32) return "pds::stft_w_kernel";
   if (plan->tc && !(plan->want_scalar && plan->fused)) {
     const bool tc2 = plan->variant == 2 && plan->N == 512;
@@ -709,6 +834,14 @@ extern "C" int pds_stft_run(pds_stft_plan* plan, const void* d_signal, int sig_d
     const int grid = (int)std::min<int64_t>(n_tiles, plan->num_sms);
     pick_ws512(plan->power, plan->row_mode)<<<grid, kWsThreads, plan->ws_smem_bytes,
                                                 static_cast<cudaStream_t>(stream)>>>(p);
+    PDS_CUDA_CHECK(cudaGetLastError());
+    return PDS_OK;
+  }
+  if (plan->um) {
+    PDS_REQUIRE(n_tiles < ((int64_t)1 << 30), "at most 2^30 tiles per launch (got %lld)", (long long)n_tiles);
+    const int grid = (int)std::min<int64_t>(n_tiles, plan->num_sms);
+    pick_umma(plan->power, sig_dtype, plan->um_nt)<<<grid, kUmThreads, plan->um_smem_bytes,
+                                                    static_cast<cudaStream_t>(stream)>>>(p);
     PDS_CUDA_CHECK(cudaGetLastError());
     return PDS_OK;
   }
