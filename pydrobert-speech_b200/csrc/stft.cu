@@ -365,8 +365,8 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     // 64 filters, operands + two sample stages in shared memory
     if (plan->tc && plan->variant == 6 && N == 512 && S % 4 == 0 && F <= 64) {
       const int kch = 2 * ((L + 63) / 64);
-      const int nt = F <= 24 ? 3 : (F <= 40 ? 5 : 8);
-      const size_t um_bytes = (size_t)um_layout(kch, p.span_max, L, nt).total;
+      const int nt = F <= 32 ? 2 : (F <= 48 ? 3 : 4);  // tiles of sixteen filters
+      const size_t um_bytes = (size_t)um_layout(kch, p.span_max, L).total;
       if (kch <= kUmMaxKch && um_bytes <= smem_cap) {
         plan->um = true;
         plan->um_smem_bytes = um_bytes;
@@ -473,7 +473,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
 
   // ---- one device blob -----------------------------------------------------------------
   // stft_umma_kernel: constant operand, window, bank fragments in the kernel's bin order (see stft_umma.cuh)
-  std::vector<unsigned char> um_amat;
+  std::vector<unsigned char> um_bmat;
   std::vector<float> um_window;
   std::vector<uint32_t> um_frags;
   std::vector<int> um_masks(4 * kUmSteps, 0), um_offs(4 * kUmSteps, 0);
@@ -481,29 +481,28 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     const int kch = p.um_kch;
     um_window.assign(N, 0.f);
     for (int i = 0; i < L; ++i) um_window[i] = d->window[i];
-    // row (TMEM lane) 32 q + 16 h + 8 im + g <-> k1 = 16 q + 8 h + g; row 8 holds Re Y[64] in place of Im Y[0].
-    // column position 8 c + k <-> j = 8 c + ((k + c) mod 8): the order in which lane c of a builder reads its samples
-    um_amat.assign(2 * (size_t)kch * kUmLboA, 0);
+    // row n of the operand = column n of D: Re Y[n] (n < 64), Re Y[64] (n = 64), Im Y[n - 64] (n > 64).
+    // K position 8 c + k <-> j = 8 c + ((k + c) mod 8): the order in which lane c of a builder reads its samples
+    um_bmat.assign(2 * (size_t)kch * kUmLboB, 0);
     for (int row = 0; row < 128; ++row) {
-      const int qq = row / 32, hh = (row / 16) % 2, im = (row / 8) % 2, gg = row % 8;
-      const int k1 = 16 * qq + 8 * hh + gg;
       for (int pos = 0; pos < 8 * kch; ++pos) {
         const int c = pos / 8, k = pos % 8, j = 8 * c + ((k + c) & 7);
         double v;
-        if (im && k1 == 0) v = (j % 2) ? -1.0 : 1.0;  // cos(pi j)
+        if (row == 64) v = (j % 2) ? -1.0 : 1.0;  // cos(pi j)
         else {
+          const int k1 = row % 64;
           const double a = two_pi * (double)((j * k1) % 128) / 128.0;
-          v = im ? -std::sin(a) : std::cos(a);
+          v = row > 64 ? -std::sin(a) : std::cos(a);
         }
         const __half hi = __float2half_rn((float)v);
         const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
-        const size_t at = (size_t)c * kUmLboA + (size_t)(row / 8) * 128 + (size_t)(row % 8) * 16 + (size_t)k * 2;
+        const size_t at = (size_t)c * kUmLboB + (size_t)(row / 8) * 128 + (size_t)(row % 8) * 16 + (size_t)k * 2;
         const unsigned short hb = __half_as_ushort(hi), lb = __half_as_ushort(lo);
-        std::memcpy(um_amat.data() + at, &hb, 2);
-        std::memcpy(um_amat.data() + (size_t)kch * kUmLboA + at, &lb, 2);
+        std::memcpy(um_bmat.data() + at, &hb, 2);
+        std::memcpy(um_bmat.data() + (size_t)kch * kUmLboB + at, &lb, 2);
       }
     }
-    // bin of k-slot kk of step s in lane quarter q (-1: none)
+    // bin of k-slot kk of bin group s at k1 = 16 qq + kk (-1: none)
     auto bin_of = [](int qq, int s, int kk) {
       const int k1 = 16 * qq + kk;
       switch (s) {
@@ -521,31 +520,36 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     };
     for (int qq = 0; qq < 4; ++qq)
       for (int s = 0; s < kUmSteps; ++s) {
-        um_offs[qq * kUmSteps + s] = (int)(um_frags.size() / 128);
+        um_offs[qq * kUmSteps + s] = (int)(um_frags.size() / 256);
         if (s == 4 && qq != 0) continue;
-        for (int nt = 0; nt < plan->um_nt; ++nt) {
+        for (int mt = 0; mt < plan->um_nt; ++mt) {
           bool any = false;
           for (int kk = 0; kk < 16 && !any; ++kk)
-            for (int gg = 0; gg < 8 && !any; ++gg) any = weight(8 * nt + gg, bin_of(qq, s, kk)) != 0.f;
+            for (int gg = 0; gg < 16 && !any; ++gg) any = weight(16 * mt + gg, bin_of(qq, s, kk)) != 0.f;
           if (!any) continue;
-          um_masks[qq * kUmSteps + s] |= 1 << nt;
+          um_masks[qq * kUmSteps + s] |= 1 << mt;
+          // mma.m16n8k16 A fragment of lane (g, t): a0 = (row g, k 2t, 2t+1), a1 = (row g + 8, same k),
+          // a2 = (row g, k 2t + 8, 2t + 9), a3 = (row g + 8, same k); high terms of 32 lanes, then low terms
+          std::vector<uint32_t> hi_part(128), lo_part(128);
           for (int ln = 0; ln < 32; ++ln) {
             const int gg = ln / 4, tt = ln % 4;
-            uint32_t hi[4], lo[4];
-            const int kks[4] = {2 * tt, 2 * tt + 1, 2 * tt + 8, 2 * tt + 9};
-            for (int i = 0; i < 4; ++i) {
-              const float w = weight(8 * nt + gg, bin_of(qq, s, kks[i]));
-              hi[i] = bf16_rn(w);
-              uint32_t hb = hi[i] << 16;
-              float hf;
-              std::memcpy(&hf, &hb, 4);
-              lo[i] = bf16_rn(w - hf);
+            for (int a = 0; a < 4; ++a) {
+              const int row = 16 * mt + gg + ((a & 1) ? 8 : 0), k0 = 2 * tt + ((a & 2) ? 8 : 0);
+              uint32_t hi[2], lo[2];
+              for (int i = 0; i < 2; ++i) {
+                const float w = weight(row, bin_of(qq, s, k0 + i));
+                hi[i] = bf16_rn(w);
+                const uint32_t hb = hi[i] << 16;
+                float hf;
+                std::memcpy(&hf, &hb, 4);
+                lo[i] = bf16_rn(w - hf);
+              }
+              hi_part[4 * ln + a] = hi[0] | (hi[1] << 16);
+              lo_part[4 * ln + a] = lo[0] | (lo[1] << 16);
             }
-            um_frags.push_back(hi[0] | (hi[1] << 16));
-            um_frags.push_back(hi[2] | (hi[3] << 16));
-            um_frags.push_back(lo[0] | (lo[1] << 16));
-            um_frags.push_back(lo[2] | (lo[3] << 16));
           }
+          um_frags.insert(um_frags.end(), hi_part.begin(), hi_part.end());
+          um_frags.insert(um_frags.end(), lo_part.begin(), lo_part.end());
         }
       }
   }
@@ -568,7 +572,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   size_t o_bb = align16(o_baw + sizeof(float2) * blue_aw.size());
   size_t o_btw = align16(o_bb + sizeof(float2) * blue_b.size());
   size_t o_uma = align16(o_btw + sizeof(float2) * blue_tw.size());
-  size_t o_umw = align16(o_uma + um_amat.size());
+  size_t o_umw = align16(o_uma + um_bmat.size());
   size_t o_umf = align16(o_umw + sizeof(float) * um_window.size());
   size_t o_umm = align16(o_umf + sizeof(uint32_t) * um_frags.size());
   size_t o_umo = align16(o_umm + sizeof(int) * um_masks.size());
@@ -593,7 +597,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
     std::memcpy(blob.data() + o_btw, blue_tw.data(), sizeof(float2) * blue_tw.size());
   }
   if (plan->um) {
-    std::memcpy(blob.data() + o_uma, um_amat.data(), um_amat.size());
+    std::memcpy(blob.data() + o_uma, um_bmat.data(), um_bmat.size());
     std::memcpy(blob.data() + o_umw, um_window.data(), sizeof(float) * um_window.size());
   }
   std::memcpy(blob.data() + o_umf, um_frags.data(), sizeof(uint32_t) * um_frags.size());
@@ -623,7 +627,7 @@ extern "C" int pds_stft_plan_create(const pds_stft_desc* d, int device, pds_stft
   p.tc_items = reinterpret_cast<const int4*>(base + o_tci);
   p.tc_wstart = reinterpret_cast<const int*>(base + o_tcw);
   p.tc_frags = reinterpret_cast<const float4*>(base + o_tcf);
-  p.um_amat = base + o_uma;
+  p.um_bmat = base + o_uma;
   p.um_window = reinterpret_cast<const float*>(base + o_umw);
   p.um_frags = base + o_umf;
   p.um_masks = reinterpret_cast<const int*>(base + o_umm);

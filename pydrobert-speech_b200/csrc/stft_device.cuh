@@ -78,10 +78,10 @@ struct StftParams {
   int rows_full, row_partial;  // L / (2G) full rows of the stage-1 load, and whether one more is partial
   int span_max;                // floats reserved for the staged samples
   // stft_umma_kernel (stft_umma.cuh): the constant DFT operand as fp16 (hi, lo) terms in its shared-memory
-  // layout, the unscaled zero-padded window [N], bank weights as bf16 m16n8k16 B fragments in the kernel's
-  // bin order ({b0_hi, b1_hi, b0_lo, b1_lo} per lane), and per (lane quarter, k-step) the mask of filter
-  // groups with non-zero weights and the index of their first fragment
-  const void* um_amat;
+  // layout, the unscaled zero-padded window [N], bank weights as bf16 m16n8k16 A fragments in the kernel's
+  // bin order ({a0 .. a3} of the high terms for 32 lanes, then of the low terms), and per (16 values of k1,
+  // bin group) the mask of 16-filter tiles with non-zero weights and the index of their first fragment
+  const void* um_bmat;
   const float* um_window;
   const void* um_frags;
   const int* um_masks;
@@ -2384,7 +2384,7 @@ KernelFn pick_tc_2048(bool power, int dtype, int mode);
 KernelFn pick_tc2_512(bool power, int dtype, int mode);
 KernelFn pick_tc2_probe(int which);                       // development probes (1: no bank, 2: no transform)
 KernelFn pick_w512(bool power, int mode, int nt);
-KernelFn pick_umma(bool power, int dtype, int nt);           // tcgen05 transform (stft_umma.cuh), nt in {3, 5, 8}
+KernelFn pick_umma(bool power, int dtype, int nt);           // tcgen05 transform (stft_umma.cuh), mt = tiles of 16 filters in {2, 3, 4}
 
 // frames per sub-group and pass: 2 where the registers allow it (R1 <= 16), see fft_frames
 template <int N>

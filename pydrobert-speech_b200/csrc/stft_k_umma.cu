@@ -2,14 +2,14 @@
 #include "stft_umma.cuh"
 
 namespace pds {
-template <int NT>
-static KernelFn pick_umma_nt(bool power, int dtype) {
-  if (power) return dtype == PDS_I16 ? stft_umma_kernel<true, short, NT> : stft_umma_kernel<true, float, NT>;
-  return dtype == PDS_I16 ? stft_umma_kernel<false, short, NT> : stft_umma_kernel<false, float, NT>;
+template <int MT>
+static KernelFn pick_umma_mt(bool power, int dtype) {
+  if (power) return dtype == PDS_I16 ? stft_umma_kernel<true, short, MT> : stft_umma_kernel<true, float, MT>;
+  return dtype == PDS_I16 ? stft_umma_kernel<false, short, MT> : stft_umma_kernel<false, float, MT>;
 }
-KernelFn pick_umma(bool power, int dtype, int nt) {
-  if (nt <= 3) return pick_umma_nt<3>(power, dtype);
-  if (nt <= 5) return pick_umma_nt<5>(power, dtype);
-  return pick_umma_nt<8>(power, dtype);
+KernelFn pick_umma(bool power, int dtype, int mt) {
+  if (mt <= 2) return pick_umma_mt<2>(power, dtype);
+  if (mt <= 3) return pick_umma_mt<3>(power, dtype);
+  return pick_umma_mt<4>(power, dtype);
 }
 }  // namespace pds

@@ -10,43 +10,43 @@
 //
 // Y_r[128 - k1] = conj(Y_r[k1]), so k1 = 0 ... 64 and k2 = 0 ... 3 reach every bin 0 ... 256 (bins above
 // 256 are mirrored: |X[512 - k]| = |X[k]|).  The 128 real numbers Re Y_r[0 ... 64], Im Y_r[1 ... 63]
-// of one (frame, residue) are one COLUMN of the GEMM
+// of one (frame, residue) are one ROW of the GEMM
 //
 //     D[128 x 128] = A[128 x K] * B[K x 128],   K = 8 * ceil(L / 32) (112 for 25 ms frames)
 //
-// with A the constant cosine / sine matrix and B the windowed samples of 32 frames x 4 residues.
-// float32-grade accuracy from fp16 operands: both are split into two fp16 terms (the samples after
-// a per-frame power-of-two scale that puts the frame's peak at 2^14 ... 2^15) and the products
-// A_hi B_hi + A_hi B_lo + A_lo B_hi are accumulated in float32 -- three MMAs per 16-deep K step, 21
-// per 32 frames, 1 344 tensor-core cycles.  The dropped term is 2^-22 of each product.
+// with A the windowed samples of 32 frames x 4 residues and B the constant cosine / sine matrix
+// (column n < 64: Re Y[n]; column 64: Re Y[64]; column 64 + n: Im Y[n]).  float32-grade accuracy from
+// fp16 operands: both are split into two fp16 terms (the samples after a per-frame power-of-two
+// scale that puts the frame's peak at 2^14 ... 2^15) and the products A_hi B_hi + A_lo B_hi + A_hi B_lo
+// are accumulated in float32 -- three MMAs per 16-deep K step, 21 per 32 frames, 1 344 tensor-core
+// cycles.  The dropped term is 2^-22 of each product.
 //
-// One persistent CTA per SM, three kinds of warps handing 32-frame tiles to each other through
+// One persistent CTA per SM, two kinds of warps handing 32-frame tiles to each other through
 // mbarriers only:
 //
 //   builder warps   stage the tile's samples (TMA bulk copy; reflected edges, 16-bit PCM and fused
-//                   pre-processing by hand, as in the other kernels), and write the B operand: a
+//                   pre-processing by hand, as in the other kernels), and write the A operand: a
 //                   half-warp per frame, lane c owns samples 32 c ... 32 c + 31 = eight values of
 //                   each residue = one 16-byte row piece of a core matrix per residue and term.
 //                   The window sits in registers.  Lane c reads its eight float4 in the rotated
 //                   order (k + c) mod 8, which makes the loads conflict free; the rotation permutes
-//                   K inside each group of eight, and the columns of A are permuted to match.
-//                   The energy column (compute.py:392-398) is summed on the way.
-//   MMA warp        one lane issues the tcgen05.mma of a tile into one of four 128-column stages of
-//                   tensor memory and commits to the mbarriers of the operand stage and of the
-//                   accumulator stage.
-//   epilogue warps  warp (q, mt) owns the 32 TMEM lanes 32 q ... (rows of A ordered so that these are
-//                   k1 = 16 q ... 16 q + 15, real parts in rows g, imaginary parts in rows g + 8 of
-//                   each 16-row block) and the 16 frames 16 mt ....  tcgen05.ld.16x256b hands thread
-//                   (g, t) Re and Im of Y_0 ... Y_3 at one k1 for two frames: the radix-4 butterfly and
-//                   |X|^2 run in registers.  The four bin groups k1, 128 + k1, 256 - k1, 128 - k1 are
-//                   split into two bf16 terms, transposed with movmatrix into mma.sync A fragments
-//                   (frames x bins) and contracted with the filter bank on bf16 m16n8k16 MMAs
-//                   (compute.py:416-460 as a banded matrix product; weights pre-permuted to this
-//                   bin order on the host, all-zero fragments skipped through a mask).  The four
-//                   warps of a frame group hold partial sums over their quarter of the bins; they
-//                   add them in a fixed order through one shared-memory tile (named barriers,
-//                   bitwise reproducible), the last one scales back, takes the logarithm and
-//                   writes the rows out as one contiguous, coalesced range.
+//                   K inside each group of eight, and the rows of B are permuted to match.  The
+//                   energy column (compute.py:392-398) is summed on the way and written directly.
+//                   One lane of the first builder warp issues the tile's tcgen05.mma into one of
+//                   four 128-column stages of tensor memory and commits to the mbarriers of the
+//                   operand stage and of the accumulator stage.
+//   epilogue warps  two groups of four take the tiles in turn.  Warp q of a group owns the TMEM
+//                   lanes 32 q ... = frames 8 q ... 8 q + 7 (rows ordered residue-major inside the 32).
+//                   tcgen05.ld.16x256b hands thread (g, t) Re and Im of Y_0 ... Y_3 of frame g at
+//                   k1 = 8 i + 2 t, 8 i + 2 t + 1: the radix-4 butterfly and |X|^2 run in registers
+//                   (twiddles from a small table).  The four bin groups k1, 128 + k1, 256 - k1,
+//                   128 - k1 are split into two bf16 terms, which ARE the B fragments (bins x
+//                   frames) of mma.sync m16n8k16: the filter bank is contracted as W P^T with the
+//                   weights as A fragments (compute.py:416-460 as a banded matrix product;
+//                   weights pre-permuted to this bin order on the host, all-zero fragments
+//                   skipped through a mask).  A warp sees every bin of its eight frames, so the
+//                   features leave the accumulator fragments directly: scale back, floor,
+//                   logarithm, store.
 #pragma once
 
 #include <cuda_fp16.h>
@@ -55,47 +55,42 @@
 
 namespace pds {
 
-constexpr int kUmEpiWarps = 8;
-#ifndef PDS_UM_BUILD_WARPS
-#define PDS_UM_BUILD_WARPS 8
-#endif
-constexpr int kUmBuildWarps = PDS_UM_BUILD_WARPS;
-constexpr int kUmThreads = 32 * (kUmEpiWarps + kUmBuildWarps + 1);
+constexpr int kUmEpiWarps = 8;     // two groups of four
+constexpr int kUmBuildWarps = 8;
+constexpr int kUmThreads = 32 * (kUmEpiWarps + kUmBuildWarps);
 constexpr int kUmBuildThreads = 32 * kUmBuildWarps;
 constexpr int kUmFrames = 32;      // frames per tile
-constexpr int kUmLboA = 2048;      // bytes between the two 8-deep halves of a K step of A: 16 core matrices
-constexpr int kUmLboB = 2064;      // the same for B, + 16 so that a quarter warp's 16-byte stores are conflict free
-constexpr int kUmRing = 8;         // per-frame scale / energy slots: the builders run at most five tiles ahead
-constexpr int kUmSteps = 5;        // bank k-steps per lane quarter: four bin groups + the step of bin 192
+constexpr int kUmLboA = 2064;      // bytes between the two 8-deep halves of a K step of A (samples): 16 core
+                                   // matrices + 16 so that a quarter warp's 16-byte stores are conflict free
+constexpr int kUmLboB = 2048;      // the same for B (constant matrix)
+constexpr int kUmRing = 8;         // per-frame scale slots: the builders run at most five tiles ahead
+constexpr int kUmSteps = 5;        // bank k-steps per 16 values of k1: four bin groups + the step of bin 192
 constexpr int kUmMaxKch = 16;
 
 struct UmLayout {  // byte offsets into the dynamic shared memory
-  int a, b, x, out, scale, energy, bars, tmem, total;
-  int a_term, b_term, b_stage, x_stage;  // strides
+  int b, a, x, scale, tw, steps, bars, tmem, total;
+  int a_term, b_term, a_stage, x_stage;  // strides
 };
-__host__ __device__ inline UmLayout um_layout(int kch, int span_max, int L, int nt) {
+__host__ __device__ inline UmLayout um_layout(int kch, int span_max, int L) {
   UmLayout l;
   l.a_term = kch * kUmLboA;
   l.b_term = kch * kUmLboB;
-  l.b_stage = 2 * l.b_term;
+  l.a_stage = 2 * l.a_term;
   // a frame reads 32 kch samples from its start; the span covers L of the last one
   l.x_stage = 4 * ((span_max + 32 * kch - L + 4 + 3) & ~3);
   int o = 0;
-  l.a = o, o += 2 * l.a_term;
-  l.b = o, o += 2 * l.b_stage;
+  l.b = o, o += 2 * l.b_term;
+  l.a = o, o += 2 * l.a_stage;
   l.x = o, o += 2 * l.x_stage;
-  l.out = o, o += 2 * 16 * 8 * nt * 4;
   l.scale = o, o += kUmRing * kUmFrames * 4;
-  l.energy = o, o += kUmRing * kUmFrames * 4;
+  l.tw = o, o += 64 * 3 * 8;
+  l.steps = o, o += 4 * kUmSteps * 8;
   l.bars = o, o += 16 * 8;
   l.tmem = o, o += 16;
   l.total = o;
   return l;
 }
 
-__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 __device__ __forceinline__ uint64_t um_desc(uint32_t addr, uint32_t lbo) {
   // K-major, no swizzle: 8-row x 16-byte core matrices, 128 bytes between 8-row groups
   uint64_t d = 0;
@@ -119,11 +114,6 @@ __device__ __forceinline__ void um_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                : "r"(taddr));
-}
-__device__ __forceinline__ uint32_t um_movmatrix(uint32_t x) {
-  uint32_t y;
-  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
 }
 __device__ __forceinline__ uint32_t um_pack_f16(float lower, float upper) {
   uint32_t d;
@@ -151,86 +141,76 @@ __device__ __forceinline__ void um_radix4(float y0r, float y0i, float t1r, float
   }
 }
 
-template <bool POWER, typename T, int NT>
+// MT: tiles of sixteen filters
+template <bool POWER, typename T, int MT>
 __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_constant__ StftParams p) {
   extern __shared__ __align__(128) uint8_t um_smem[];
   const int kch = p.um_kch;
-  const UmLayout lay = um_layout(kch, p.span_max, p.L, NT);
+  const UmLayout lay = um_layout(kch, p.span_max, p.L);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(um_smem + lay.bars);
-  uint64_t* const b_full = bars;        // [2] builders -> MMA
-  uint64_t* const b_empty = bars + 2;   // [2] MMA done with the operand stage -> builders
+  uint64_t* const a_full = bars;        // [2] builders -> MMA issuer
+  uint64_t* const a_empty = bars + 2;   // [2] MMAs done with the operand stage -> builders
   uint64_t* const d_full = bars + 4;    // [4] accumulators complete -> epilogue
-  uint64_t* const d_empty = bars + 8;   // [4] epilogue has read the accumulators -> MMA
+  uint64_t* const d_empty = bars + 8;   // [4] epilogue has read the accumulators -> MMA issuer
   uint64_t* const x_full = bars + 12;   // [2] sample stage arrived
   uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(um_smem + lay.tmem);
   float* const s_scale = reinterpret_cast<float*>(um_smem + lay.scale);
-  float* const s_energy = reinterpret_cast<float*>(um_smem + lay.energy);
+  float2* const s_tw = reinterpret_cast<float2*>(um_smem + lay.tw);
+  int2* const s_steps = reinterpret_cast<int2*>(um_smem + lay.steps);  // {mask of filter tiles, first fragment}
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = (int)p.n_tiles, stride = gridDim.x;
-  const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + stride - 1) / stride : 0;
+  const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + stride - 1) / stride : 0;
 
   // ---- one-time set-up ---------------------------------------------------------------------
   {
-    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(p.um_amat);
-    uint4* dst = reinterpret_cast<uint4*>(um_smem + lay.a);
-    for (int i = tid; i < 2 * lay.a_term / 16; i += kUmThreads) dst[i] = src[i];
-    uint4* zero = reinterpret_cast<uint4*>(um_smem + lay.b);
-    for (int i = tid; i < (2 * lay.b_stage + 2 * lay.x_stage) / 16; i += kUmThreads) zero[i] = make_uint4(0, 0, 0, 0);
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(p.um_bmat);
+    uint4* dst = reinterpret_cast<uint4*>(um_smem + lay.b);
+    for (int i = tid; i < 2 * lay.b_term / 16; i += kUmThreads) dst[i] = src[i];
+    uint4* zero = reinterpret_cast<uint4*>(um_smem + lay.a);
+    for (int i = tid; i < (2 * lay.a_stage + 2 * lay.x_stage) / 16; i += kUmThreads) zero[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 64 * 3; i += kUmThreads) {  // W_512^(r k1) at [k1][r - 1]
+      float sn, cs;
+      sincospif((float)((i % 3 + 1) * (i / 3)) * (1.0f / 256.0f), &sn, &cs);
+      s_tw[i] = make_float2(cs, -sn);
+    }
+    if (tid < 4 * kUmSteps) s_steps[tid] = make_int2(p.um_masks[tid], p.um_offs[tid]);
   }
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) mbar_init(b_full + i, kUmBuildWarps), mbar_init(b_empty + i, 1), mbar_init(x_full + i, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(d_full + i, 1), mbar_init(d_empty + i, kUmEpiWarps);
+    for (int i = 0; i < 2; ++i) mbar_init(a_full + i, kUmBuildWarps), mbar_init(a_empty + i, 1), mbar_init(x_full + i, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(d_full + i, 1), mbar_init(d_empty + i, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kUmEpiWarps + kUmBuildWarps) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s_tmem)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // A and the zeroed B stages -> async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // B and the zeroed A stages -> async proxy
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *s_tmem;
 
-  if (warp == kUmEpiWarps + kUmBuildWarps) {
-    // ======================================= MMA warp =======================================
-    const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(128 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
-    const uint32_t a_hi = smem_u32(um_smem + lay.a), a_lo = a_hi + lay.a_term;
-    for (int it = 0; it < my_tiles; ++it) {
-      if (lane == 0) {
-        const int bs = it & 1, ts = it & 3;
-        mbar_wait(b_full + bs, (it >> 1) & 1);
-        mbar_wait(d_empty + ts, ((it >> 2) & 1) ^ 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t b_hi = smem_u32(um_smem + lay.b + bs * lay.b_stage), b_lo = b_hi + lay.b_term;
-        const uint32_t d = tmem + 128 * ts;
-        for (int s = 0; s < kch / 2; ++s) {
-          const uint64_t ah = um_desc(a_hi + s * 2 * kUmLboA, kUmLboA), al = um_desc(a_lo + s * 2 * kUmLboA, kUmLboA);
-          const uint64_t bh = um_desc(b_hi + s * 2 * kUmLboB, kUmLboB), bl = um_desc(b_lo + s * 2 * kUmLboB, kUmLboB);
-          um_mma(d, ah, bh, idesc, s > 0);
-          um_mma(d, ah, bl, idesc, 1);
-          um_mma(d, al, bh, idesc, 1);
-        }
-        um_commit(b_empty + bs);
-        um_commit(d_full + ts);
-      }
-      __syncwarp();
-    }
-  } else if (warp >= kUmEpiWarps) {
+  if (warp >= kUmEpiWarps) {
     // ===================================== builder warps ====================================
     const int bw = warp - kUmEpiWarps, btid = tid - 32 * kUmEpiWarps;
     const int c = lane & 15, hw = lane >> 4;
-    const bool lane_on = c < kch;
     const T* __restrict__ sig = static_cast<const T*>(p.sig);
+    const int valid = min(max(p.L - 32 * c, 0), 32);  // samples of this lane inside the frame
+    const bool lane_on = c < kch && valid > 0;
     float wreg[8][4];
+    bool k_on[8];  // float4 (k + c) mod 8 of this lane starts inside the frame
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float4 w4 = lane_on ? *reinterpret_cast<const float4*>(p.um_window + 32 * c + 4 * ((k + c) & 7))
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int at = 4 * ((k + c) & 7);
+      k_on[k] = lane_on && at < valid;
+      const float4 w4 = k_on[k] ? *reinterpret_cast<const float4*>(p.um_window + 32 * c + at) : make_float4(0.f, 0.f, 0.f, 0.f);
       wreg[k][0] = w4.x, wreg[k][1] = w4.y, wreg[k][2] = w4.z, wreg[k][3] = w4.w;
     }
-    const int valid = min(max(p.L - 32 * c, 0), 32);  // samples of this lane inside the frame (energy)
+    const bool ragged = (valid & 3) != 0;  // frame lengths that are not a multiple of four: per-sample mask
+    const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(128 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+    const uint32_t b_hi = smem_u32(um_smem + lay.b), b_lo = b_hi + lay.b_term;
+    const bool want_energy = p.include_energy != 0;
 
     // prologue: samples of the first tile
     pds_tile next = p.tiles[blockIdx.x];
@@ -251,7 +231,7 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
     }
     for (int it = 0; it < my_tiles; ++it) {
       const pds_tile tile = next;
-      const int bs = it & 1;
+      const int as = it & 1, ts = it & 3;
       // every builder is done with the other sample stage; hand-staged samples of this tile are visible
       named_bar_sync(1, kUmBuildThreads);
       if (it + 1 < my_tiles) {
@@ -271,22 +251,22 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
         }
         if (a1 - a0 < span) stage_samples_slow<T, kUmBuildThreads>(s_xn, p, next, span, a0, a1, btid);
       }
-      mbar_wait(x_full + bs, (it >> 1) & 1);
-      mbar_wait(b_empty + bs, ((it >> 1) & 1) ^ 1);
-      const float* __restrict__ s_x = reinterpret_cast<const float*>(um_smem + lay.x + bs * lay.x_stage);
-      uint8_t* const b_stage = um_smem + lay.b + bs * lay.b_stage;
+      mbar_wait(x_full + as, (it >> 1) & 1);
+      mbar_wait(a_empty + as, ((it >> 1) & 1) ^ 1);
+      const float* __restrict__ s_x = reinterpret_cast<const float*>(um_smem + lay.x + as * lay.x_stage);
+      uint8_t* const a_stage = um_smem + lay.a + as * lay.a_stage;
       const int ring = (it & (kUmRing - 1)) * kUmFrames;
 #pragma unroll 1
       for (int f = 2 * bw + hw; f < kUmFrames; f += 2 * kUmBuildWarps) {
-        const bool on = lane_on && f < tile.nframes;
+        const bool on = f < tile.nframes;
         const float* fx = s_x + f * p.S + 32 * c;
         float v[8][4];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float4 q = on ? *reinterpret_cast<const float4*>(fx + 4 * ((k + c) & 7)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 q = (on && k_on[k]) ? *reinterpret_cast<const float4*>(fx + 4 * ((k + c) & 7)) : make_float4(0.f, 0.f, 0.f, 0.f);
           v[k][0] = q.x, v[k][1] = q.y, v[k][2] = q.z, v[k][3] = q.w;
         }
-        if (valid != 32) {  // the lane that holds the end of the frame (and the lanes past it)
+        if (ragged) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
 #pragma unroll
@@ -310,8 +290,8 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
         // power-of-two scale: peak * s in [2^14, 2^15); s in [2^-49, 2^60] so that 1 / s^2 stays normal
         const int sb = min(max(268 - (int)(__float_as_uint(peak) >> 23), 78), 187);
         const float s = __uint_as_float((uint32_t)sb << 23);
-        if (on) {
-          uint8_t* const dst = b_stage + c * kUmLboB + (4 * (f >> 3)) * 128 + (f & 7) * 16;
+        if (on && lane_on) {
+          uint8_t* const dst = a_stage + c * kUmLboA + (4 * (f >> 3)) * 128 + (f & 7) * 16;
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             uint32_t hi[4], lo[4];
@@ -324,190 +304,175 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
               lo[m] = um_pack_f16(x0 - h0, x1 - h1);
             }
             *reinterpret_cast<uint4*>(dst + r * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(dst + r * 128 + lay.b_term) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(dst + r * 128 + lay.a_term) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           if (c == 0) {
             const float inv = __uint_as_float((uint32_t)(254 - sb) << 23);
             s_scale[ring + f] = POWER ? inv * inv : inv;
-            s_energy[ring + f] = en;
+            if (want_energy) {  // energy column (compute.py:392-398)
+              float e = en * p.inv_L;
+              if (!POWER) e = sqrtf(e);
+              if (p.use_log) e = fast_log(fmaxf(e, p.log_floor));
+              __stcs(p.out + (tile.out_row + f) * p.C, e);
+            }
           }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the operand stores -> async proxy (MMA)
       __syncwarp();
-      if (lane == 0) mbar_arrive(b_full + bs);
+      if (lane == 0) mbar_arrive(a_full + as);
+      if (bw == 0) {
+        // ---- the tile's MMAs: D[ts] = A[as] * B ------------------------------------------------
+        if (lane == 0) {
+          mbar_wait(a_full + as, (it >> 1) & 1);
+          mbar_wait(d_empty + ts, ((it >> 2) & 1) ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_u32(a_stage), a_lo = a_hi + lay.a_term;
+          const uint32_t d = tmem + 128 * ts;
+          for (int st = 0; st < kch / 2; ++st) {
+            const uint64_t ah = um_desc(a_hi + st * 2 * kUmLboA, kUmLboA), al = um_desc(a_lo + st * 2 * kUmLboA, kUmLboA);
+            const uint64_t bh = um_desc(b_hi + st * 2 * kUmLboB, kUmLboB), bl = um_desc(b_lo + st * 2 * kUmLboB, kUmLboB);
+            um_mma(d, ah, bh, idesc, st > 0);
+            um_mma(d, al, bh, idesc, 1);
+            um_mma(d, ah, bl, idesc, 1);
+          }
+          um_commit(a_empty + as);
+          um_commit(d_full + ts);
+        }
+        __syncwarp();
+      }
     }
   } else {
     // ===================================== epilogue warps ===================================
-    const int q = warp & 3, mt = warp >> 2;
+    const int q = warp & 3, grp = warp >> 2;
     const int g = lane >> 2, t = lane & 3;
-    float twr[2][3], twi[2][3];  // W_512^(r k1), r = 1 ... 3, at k1 = 16 q + 8 h + g
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-      for (int r = 1; r < 4; ++r) {
-        float sn, cs;
-        sincospif((float)(r * (16 * q + 8 * h + g)) * (1.0f / 256.0f), &sn, &cs);
-        twr[h][r - 1] = cs, twi[h][r - 1] = -sn;
-      }
-    int masks[kUmSteps], offs[kUmSteps];
-#pragma unroll
-    for (int s = 0; s < kUmSteps; ++s) masks[s] = p.um_masks[q * kUmSteps + s], offs[s] = p.um_offs[q * kUmSteps + s];
-    const bool special = q == 0 && g == 0;  // k1 = 0: the imaginary row holds Re Y[64]
-    float* const s_out = reinterpret_cast<float*>(um_smem + lay.out) + mt * 16 * 8 * NT;
-    const int id_turn = 2 + 4 * mt, id_free = 2 + 4 * mt + 3;
-    const uint4* __restrict__ frags = reinterpret_cast<const uint4*>(p.um_frags);
+    const uint4* __restrict__ frags = reinterpret_cast<const uint4*>(p.um_frags) + lane;
     const bool use_log = p.use_log != 0;
+    const float log_floor = p.log_floor;
+    const int C = p.C, e_col = p.include_energy, F = p.F;
 
-    for (int it = 0; it < my_tiles; ++it) {
+    for (int it = grp; it < my_tiles; it += 2) {
       const int ts = it & 3;
       const pds_tile tile = p.tiles[blockIdx.x + (long long)it * stride];
       mbar_wait(d_full + ts, (it >> 2) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t fh[4][4], fl[4][4], xh[2] = {0u, 0u}, xl[2] = {0u, 0u};
+      float acc[MT][4];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[2][16];
-        const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * q + 16 * h) << 16) + 128 * ts + 64 * mt;
+      for (int m = 0; m < MT; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+      float p192 = 0.f;
+#pragma unroll
+      for (int rd = 0; rd < 2; ++rd) {
+        // rows g (residue 0 / 2) and g + 8 (residue 1 / 3) of the two 16-lane blocks; real parts at
+        // columns k1, imaginary parts at 64 + k1; this round: k1 = 32 rd + 8 i + 2 t + e
+        uint32_t v[4][16];
+        const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * q) << 16) + 128 * ts + 32 * rd;
         um_ld16(taddr, v[0]);
-        um_ld16(taddr + 32, v[1]);
+        um_ld16(taddr + 64, v[1]);
+        um_ld16(taddr + (16u << 16), v[2]);
+        um_ld16(taddr + (16u << 16) + 64, v[3]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (rd == 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d_empty + ts);
+        }
 #pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          float pw[2][4], p64[2] = {0.f, 0.f}, p192[2] = {0.f, 0.f};
+        for (int sp = 0; sp < 2; ++sp) {
+          float pw[2][2][4];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            float yr[4], yi[4];
+          for (int ii = 0; ii < 2; ++ii) {
+            const int i = 2 * sp + ii;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) yr[r] = __uint_as_float(v[o][4 * r + e]), yi[r] = __uint_as_float(v[o][4 * r + 2 + e]);
-            if (h == 0 && special) {
-              // k1 = 64 from the purely real Y_r[64] (twiddles exp(-i pi r / 4)), then k1 = 0 with Im Y = 0
-              const float c4 = 0.70710678118654752f;
-              float q4[4];
-              um_radix4<POWER>(yi[0], 0.f, c4 * yi[1], -c4 * yi[1], 0.f, -yi[2], -c4 * yi[3], -c4 * yi[3], q4);
-              p64[e] = q4[0], p192[e] = q4[1];
+            for (int e = 0; e < 2; ++e) {
+              float yr[4], yi[4];
 #pragma unroll
-              for (int r = 0; r < 4; ++r) yi[r] = 0.f;
+              for (int r = 0; r < 4; ++r) {
+                yr[r] = __uint_as_float(v[2 * (r >> 1)][4 * i + 2 * (r & 1) + e]);
+                yi[r] = __uint_as_float(v[2 * (r >> 1) + 1][4 * i + 2 * (r & 1) + e]);
+              }
+              bool special = false;
+              float p64 = 0.f;
+              if (rd == 0 && i == 0 && e == 0) {
+                special = t == 0;  // k1 = 0: the imaginary column holds Re Y[64]
+                if (special) {
+                  // k1 = 64 from the purely real Y_r[64] (twiddles exp(-i pi r / 4)), then k1 = 0 with Im Y = 0
+                  const float c4 = 0.70710678118654752f;
+                  float q4[4];
+                  um_radix4<POWER>(yi[0], 0.f, c4 * yi[1], -c4 * yi[1], 0.f, -yi[2], -c4 * yi[3], -c4 * yi[3], q4);
+                  p64 = q4[0], p192 = q4[1];
+#pragma unroll
+                  for (int r = 0; r < 4; ++r) yi[r] = 0.f;
+                }
+              }
+              const float2* __restrict__ tw = s_tw + 3 * (32 * rd + 8 * i + 2 * t + e);
+              float tr[3], ti[3];
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                const float2 w = tw[r];
+                tr[r] = yr[r + 1] * w.x - yi[r + 1] * w.y;
+                ti[r] = yr[r + 1] * w.y + yi[r + 1] * w.x;
+              }
+              um_radix4<POWER>(yr[0], yi[0], tr[0], ti[0], tr[1], ti[1], tr[2], ti[2], pw[ii][e]);
+              if (rd == 0 && i == 0 && e == 0 && special) pw[ii][e][3] = p64;  // the slot of the duplicate bin 128 carries bin 64
             }
-            float tr[3], ti[3];
+          }
+          // ---- filter bank: this k-step of the four bin groups (+ bin 192 once) ----------------
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              tr[r] = yr[r + 1] * twr[h][r] - yi[r + 1] * twi[h][r];
-              ti[r] = yr[r + 1] * twi[h][r] + yi[r + 1] * twr[h][r];
+          for (int grp4 = 0; grp4 < kUmSteps; ++grp4) {
+            if (grp4 == 4 && !(rd == 0 && sp == 0)) continue;
+            uint32_t b0h, b0l, b1h, b1l;
+            if (grp4 < 4) {
+              split_bf16x2(pw[0][0][grp4 & 3], pw[0][1][grp4 & 3], b0h, b0l);
+              split_bf16x2(pw[1][0][grp4 & 3], pw[1][1][grp4 & 3], b1h, b1l);
+            } else {
+              split_bf16x2(p192, 0.f, b0h, b0l);  // k = 0 of the extra step (non-zero in the lanes t = 0 only)
+              b1h = b1l = 0u;
             }
-            um_radix4<POWER>(yr[0], yi[0], tr[0], ti[0], tr[1], ti[1], tr[2], ti[2], pw[e]);
-            if (h == 0 && special) pw[e][3] = p64[e];  // the slot of the duplicate bin 128 carries bin 64
-          }
+            const int2 step = s_steps[(2 * rd + sp) * kUmSteps + grp4];
+            const int mask = step.x;
+            const uint4* __restrict__ fr = frags + (size_t)step.y * 64;
 #pragma unroll
-          for (int grp = 0; grp < 4; ++grp) {
-            uint32_t hi, lo;
-            split_bf16x2(pw[0][grp], pw[1][grp], hi, lo);
-            fh[grp][2 * h + o] = um_movmatrix(hi);
-            fl[grp][2 * h + o] = um_movmatrix(lo);
-          }
-          if (h == 0 && q == 0) {  // warp-uniform: bin 192 as k = 0 of the extra step
-            uint32_t hi, lo;
-            split_bf16x2(p192[0], p192[1], hi, lo);
-            xh[o] = um_movmatrix(hi);
-            xl[o] = um_movmatrix(lo);
+            for (int m = 0; m < MT; ++m) {
+              if ((mask >> m) & 1) {
+                const uint4 wh = __ldg(fr), wl = __ldg(fr + 32);
+                fr += 64;
+                mma_bf16(acc[m], wh.x, wh.y, wh.z, wh.w, b0h, b1h);
+                mma_bf16(acc[m], wh.x, wh.y, wh.z, wh.w, b0l, b1l);
+                mma_bf16(acc[m], wl.x, wl.y, wl.z, wl.w, b0h, b1h);
+              }
+            }
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(d_empty + ts);
-
-      // ---- filter bank: partial sums over this warp's quarter of the bins -----------------
-      float acc[NT][4];
+      // ---- features of frames 8 q + 2 t, + 1 and filters 16 m + g, + 8: scale back, floor, log, store
+      const int ring = (it & (kUmRing - 1)) * kUmFrames + 8 * q + 2 * t;
+      const float sc0 = s_scale[ring], sc1 = s_scale[ring + 1];
+      const int fr0 = 8 * q + 2 * t;
+      float* __restrict__ dst = p.out + (tile.out_row + fr0) * C + e_col + g;
+      const bool ok0 = fr0 < tile.nframes, ok1 = fr0 + 1 < tile.nframes;
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+      for (int m = 0; m < MT; ++m) {
+        float o[4] = {acc[m][0] * sc0, acc[m][1] * sc1, acc[m][2] * sc0, acc[m][3] * sc1};
+        if (use_log) {
 #pragma unroll
-      for (int s = 0; s < kUmSteps; ++s) {
-        if (s == 4 && q != 0) break;
-        const int mask = masks[s];
-        const uint4* __restrict__ fr = frags + (size_t)offs[s] * 32 + lane;
-        uint32_t ah[4], al[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          ah[j] = s < 4 ? fh[s < 4 ? s : 0][j] : (j < 2 ? xh[j] : 0u);
-          al[j] = s < 4 ? fl[s < 4 ? s : 0][j] : (j < 2 ? xl[j] : 0u);
+          for (int i = 0; i < 4; ++i) o[i] = fast_log(fmaxf(o[i], log_floor));
         }
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          if ((mask >> nt) & 1) {
-            const uint4 w = __ldg(fr);
-            fr += 32;
-            mma_bf16(acc[nt], ah[0], ah[1], ah[2], ah[3], w.x, w.y);
-            mma_bf16(acc[nt], al[0], al[1], al[2], al[3], w.x, w.y);
-            mma_bf16(acc[nt], ah[0], ah[1], ah[2], ah[3], w.z, w.w);
-          }
+        const int f0 = 16 * m + g;
+        if (f0 < F) {
+          if (ok0) __stcs(dst + 16 * m, o[0]);
+          if (ok1) __stcs(dst + 16 * m + C, o[1]);
         }
-      }
-
-      // ---- the four quarters add up in the order q = 0, 1, 2, 3 -----------------------------
-      float* const row0 = s_out + g * 8 * NT + 2 * t;
-      float* const row1 = row0 + 8 * 8 * NT;
-      if (q == 0) {
-        if (it > 0) named_bar_sync(id_free, 64);
-      } else {
-        named_bar_sync(id_turn + q - 1, 64);
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const float2 u0 = *reinterpret_cast<const float2*>(row0 + 8 * nt), u1 = *reinterpret_cast<const float2*>(row1 + 8 * nt);
-          acc[nt][0] += u0.x, acc[nt][1] += u0.y, acc[nt][2] += u1.x, acc[nt][3] += u1.y;
+        if (f0 + 8 < F) {
+          if (ok0) __stcs(dst + 16 * m + 8, o[2]);
+          if (ok1) __stcs(dst + 16 * m + 8 + C, o[3]);
         }
-      }
-      if (q == 3) {
-        const int ring = (it & (kUmRing - 1)) * kUmFrames + 16 * mt;
-        const float sc0 = s_scale[ring + g], sc1 = s_scale[ring + g + 8];
-        const float log_floor = p.log_floor;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          acc[nt][0] *= sc0, acc[nt][1] *= sc0, acc[nt][2] *= sc1, acc[nt][3] *= sc1;
-          if (use_log) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[nt][i] = fast_log(fmaxf(acc[nt][i], log_floor));
-          }
-        }
-      }
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        *reinterpret_cast<float2*>(row0 + 8 * nt) = make_float2(acc[nt][0], acc[nt][1]);
-        *reinterpret_cast<float2*>(row1 + 8 * nt) = make_float2(acc[nt][2], acc[nt][3]);
-      }
-      if (q < 3) {
-        __threadfence_block();
-        named_bar_arrive(id_turn + q, 64);
-      } else {
-        __syncwarp();
-        // rows of the tile are consecutive in the output: one contiguous range, energy column first
-        const int rows = min(16, tile.nframes - 16 * mt);
-        const int C = p.C, e_col = p.include_energy;
-        float* __restrict__ dst = p.out + (tile.out_row + 16 * mt) * C;
-        const int ring = (it & (kUmRing - 1)) * kUmFrames + 16 * mt;
-        for (int idx = lane; idx < rows * C; idx += 32) {
-          const int fr = idx / C, col = idx - fr * C;
-          float val;
-          if (col < e_col) {
-            val = s_energy[ring + fr] * p.inv_L;
-            if (!POWER) val = sqrtf(val);
-            if (use_log) val = fast_log(fmaxf(val, p.log_floor));
-          } else {
-            val = s_out[fr * 8 * NT + col - e_col];
-          }
-          __stcs(dst + idx, val);
-        }
-        __syncwarp();
-        named_bar_arrive(id_free, 64);
       }
     }
-    if (q == 0 && my_tiles > 0) named_bar_sync(id_free, 64);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == kUmEpiWarps + kUmBuildWarps)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
 }
 
 }  // namespace pds
