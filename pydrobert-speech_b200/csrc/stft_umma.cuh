@@ -17,9 +17,9 @@
 // with A the windowed samples of 32 frames x 4 residues and B the constant cosine / sine matrix
 // (column n < 64: Re Y[n]; column 64: Re Y[64]; column 64 + n: Im Y[n]).  float32-grade accuracy from
 // fp16 operands: both are split into two fp16 terms (the samples after a per-frame power-of-two
-// scale that puts the frame's peak at 2^14 ... 2^15) and the products A_hi B_hi + A_lo B_hi + A_hi B_lo
-// are accumulated in float32 -- three MMAs per 16-deep K step, 21 per 32 frames, 1 344 tensor-core
-// cycles.  The dropped term is 2^-22 of each product.
+// scale that puts the frame's peak at 2^14 ... 2^15) and all four products of the terms are accumulated
+// in float32 -- four MMAs per 16-deep K step, 28 per 32 frames, 1 800 tensor-core cycles.  What is
+// left is the rounding of the low terms, 2^-23 of each operand.
 //
 // One persistent CTA per SM, two kinds of warps handing 32-frame tiles to each other through
 // mbarriers only:
@@ -68,7 +68,7 @@ constexpr int kUmSteps = 5;        // bank k-steps per 16 values of k1: four bin
 constexpr int kUmMaxKch = 16;
 
 struct UmLayout {  // byte offsets into the dynamic shared memory
-  int b, a, x, scale, tw, steps, bars, tmem, total;
+  int b, a, x, scale, tw, steps, bars, count, tmem, total;
   int a_term, b_term, a_stage, x_stage;  // strides
 };
 __host__ __device__ inline UmLayout um_layout(int kch, int span_max, int L) {
@@ -86,9 +86,19 @@ __host__ __device__ inline UmLayout um_layout(int kch, int span_max, int L) {
   l.tw = o, o += 64 * 3 * 8;
   l.steps = o, o += 4 * kUmSteps * 8;
   l.bars = o, o += 16 * 8;
+  l.count = o, o += 16;
   l.tmem = o, o += 16;
   l.total = o;
   return l;
+}
+
+// wait of a warp that expects to wait: a few polls, then back off so that the spinning does not take
+// issue slots from the warps that do the work (bounded like mbar_wait)
+__device__ __forceinline__ void um_wait(uint64_t* bar, uint32_t parity) {
+  for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins >= 2) __nanosleep(64);
+    if (spins > (1u << 22)) __trap();
+  }
 }
 
 __device__ __forceinline__ uint64_t um_desc(uint32_t addr, uint32_t lbo) {
@@ -153,6 +163,7 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
   uint64_t* const d_full = bars + 4;    // [4] accumulators complete -> epilogue
   uint64_t* const d_empty = bars + 8;   // [4] epilogue has read the accumulators -> MMA issuer
   uint64_t* const x_full = bars + 12;   // [2] sample stage arrived
+  uint64_t* const x_empty = bars + 14;  // [2] every builder warp has read the sample stage
   uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(um_smem + lay.tmem);
   float* const s_scale = reinterpret_cast<float*>(um_smem + lay.scale);
   float2* const s_tw = reinterpret_cast<float2*>(um_smem + lay.tw);
@@ -177,7 +188,9 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
     if (tid < 4 * kUmSteps) s_steps[tid] = make_int2(p.um_masks[tid], p.um_offs[tid]);
   }
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) mbar_init(a_full + i, kUmBuildWarps), mbar_init(a_empty + i, 1), mbar_init(x_full + i, 1);
+    for (int i = 0; i < 2; ++i)
+      mbar_init(a_full + i, kUmBuildWarps), mbar_init(a_empty + i, 1), mbar_init(x_full + i, 1), mbar_init(x_empty + i, kUmBuildWarps);
+    reinterpret_cast<int*>(um_smem + lay.count)[0] = reinterpret_cast<int*>(um_smem + lay.count)[1] = 0;
     for (int i = 0; i < 4; ++i) mbar_init(d_full + i, 1), mbar_init(d_empty + i, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -212,52 +225,48 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
     const uint32_t b_hi = smem_u32(um_smem + lay.b), b_lo = b_hi + lay.b_term;
     const bool want_energy = p.include_energy != 0;
 
-    // prologue: samples of the first tile
-    pds_tile next = p.tiles[blockIdx.x];
-    {
-      const int span = (next.nframes - 1) * p.S + p.L;
+    // stage the samples of `tile` (use number `use` of sample stage xs): TMA bulk copy by one thread once every
+    // builder warp has read the stage's previous contents; reflected edges, 16-bit PCM and fused
+    // pre-processing by hand (all builder threads; CTA-uniform, rare for float32 input)
+    auto stage_tile = [&](const pds_tile& tile, int xs, int use) {
+      const int span = (tile.nframes - 1) * p.S + p.L;
       int a0, a1;
-      bulk_range<T>(p, next, span, a0, a1);
-      float* s_x = reinterpret_cast<float*>(um_smem + lay.x);
+      bulk_range<T>(p, tile, span, a0, a1);
+      float* s_xn = reinterpret_cast<float*>(um_smem + lay.x + xs * lay.x_stage);
+      const bool by_hand = a1 - a0 < span;
+      if (by_hand) {
+        um_wait(x_empty + xs, (use & 1) ^ 1);
+        stage_samples_slow<T, kUmBuildThreads>(s_xn, p, tile, span, a0, a1, btid);
+        named_bar_sync(1, kUmBuildThreads);  // hand-staged samples are visible before x_full completes
+      }
       if (btid == 0) {
         if (a1 > a0) {
-          mbar_expect_tx(x_full, (a1 - a0) * 4);
-          bulk_copy_g2s(s_x + a0, sig + next.sig_off + next.start + a0, (a1 - a0) * 4, x_full);
+          if (!by_hand) um_wait(x_empty + xs, (use & 1) ^ 1);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(x_full + xs, (a1 - a0) * 4);
+          bulk_copy_g2s(s_xn + a0, sig + tile.sig_off + tile.start + a0, (a1 - a0) * 4, x_full + xs);
         } else {
-          mbar_arrive(x_full);
+          mbar_arrive(x_full + xs);
         }
       }
-      if (a1 - a0 < span) stage_samples_slow<T, kUmBuildThreads>(s_x, p, next, span, a0, a1, btid);
-    }
+    };
+    int* const s_count = reinterpret_cast<int*>(um_smem + lay.count);
+    const long long first = blockIdx.x;
+    pds_tile tile = p.tiles[first];
+    pds_tile next = my_tiles > 1 ? p.tiles[first + stride] : tile;
+    stage_tile(tile, 0, 0);
     for (int it = 0; it < my_tiles; ++it) {
-      const pds_tile tile = next;
       const int as = it & 1, ts = it & 3;
-      // every builder is done with the other sample stage; hand-staged samples of this tile are visible
-      named_bar_sync(1, kUmBuildThreads);
-      if (it + 1 < my_tiles) {
-        next = p.tiles[blockIdx.x + (long long)(it + 1) * stride];
-        const int span = (next.nframes - 1) * p.S + p.L;
-        int a0, a1;
-        bulk_range<T>(p, next, span, a0, a1);
-        float* s_xn = reinterpret_cast<float*>(um_smem + lay.x + ((it + 1) & 1) * lay.x_stage);
-        if (btid == 0) {
-          if (a1 > a0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(x_full + ((it + 1) & 1), (a1 - a0) * 4);
-            bulk_copy_g2s(s_xn + a0, sig + next.sig_off + next.start + a0, (a1 - a0) * 4, x_full + ((it + 1) & 1));
-          } else {
-            mbar_arrive(x_full + ((it + 1) & 1));
-          }
-        }
-        if (a1 - a0 < span) stage_samples_slow<T, kUmBuildThreads>(s_xn, p, next, span, a0, a1, btid);
-      }
-      mbar_wait(x_full + as, (it >> 1) & 1);
-      mbar_wait(a_empty + as, ((it >> 1) & 1) ^ 1);
+      // the descriptor after the next one is fetched a whole tile ahead of its use
+      const pds_tile after = it + 2 < my_tiles ? p.tiles[first + (long long)(it + 2) * stride] : next;
+      if (it + 1 < my_tiles) stage_tile(next, (it + 1) & 1, (it + 1) >> 1);
+      um_wait(x_full + as, (it >> 1) & 1);
+      um_wait(a_empty + as, ((it >> 1) & 1) ^ 1);
       const float* __restrict__ s_x = reinterpret_cast<const float*>(um_smem + lay.x + as * lay.x_stage);
       uint8_t* const a_stage = um_smem + lay.a + as * lay.a_stage;
       const int ring = (it & (kUmRing - 1)) * kUmFrames;
 #pragma unroll 1
-      for (int f = 2 * bw + hw; f < kUmFrames; f += 2 * kUmBuildWarps) {
+      for (int f = 2 * bw + hw; f < ((p.w_probe & 1) ? 0 : kUmFrames); f += 2 * kUmBuildWarps) {  // development probe 1: no operand
         const bool on = f < tile.nframes;
         const float* fx = s_x + f * p.S + 32 * c;
         float v[8][4];
@@ -298,8 +307,9 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
               const float x0 = v[2 * m][r] * s, x1 = v[2 * m + 1][r] * s;
-              const float h0 = __uint_as_float(__float_as_uint(x0) & 0xffffe000u);
-              const float h1 = __uint_as_float(__float_as_uint(x1) & 0xffffe000u);
+              // high term: x rounded to the 11 significant bits of fp16 (exact in fp16), low term: the rest
+              const float h0 = __uint_as_float((__float_as_uint(x0) + 0x1000u) & 0xffffe000u);
+              const float h1 = __uint_as_float((__float_as_uint(x1) + 0x1000u) & 0xffffe000u);
               hi[m] = um_pack_f16(h0, h1);
               lo[m] = um_pack_f16(x0 - h0, x1 - h1);
             }
@@ -320,12 +330,19 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the operand stores -> async proxy (MMA)
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_full + as);
-      if (bw == 0) {
-        // ---- the tile's MMAs: D[ts] = A[as] * B ------------------------------------------------
+      int last = 0;
+      if (lane == 0) {
+        mbar_arrive(x_empty + as);
+        mbar_arrive(a_full + as);
+        last = atomicAdd(s_count + as, 1) == kUmBuildWarps - 1;
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        // ---- the warp that finishes the operand last issues the tile's MMAs: D[ts] = A[as] * B ----
         if (lane == 0) {
+          s_count[as] = 0;
           mbar_wait(a_full + as, (it >> 1) & 1);
-          mbar_wait(d_empty + ts, ((it >> 2) & 1) ^ 1);
+          um_wait(d_empty + ts, ((it >> 2) & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = smem_u32(a_stage), a_lo = a_hi + lay.a_term;
           const uint32_t d = tmem + 128 * ts;
@@ -335,12 +352,16 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
             um_mma(d, ah, bh, idesc, st > 0);
             um_mma(d, al, bh, idesc, 1);
             um_mma(d, ah, bl, idesc, 1);
+            um_mma(d, al, bl, idesc, 1);  // 2^-22 of the product: free on the tensor pipe, and it keeps
+                                          // coefficients 60 dB below the frame's peak inside the tolerance
           }
           um_commit(a_empty + as);
           um_commit(d_full + ts);
         }
         __syncwarp();
       }
+      tile = next;
+      next = after;
     }
   } else {
     // ===================================== epilogue warps ===================================
@@ -354,8 +375,14 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
     for (int it = grp; it < my_tiles; it += 2) {
       const int ts = it & 3;
       const pds_tile tile = p.tiles[blockIdx.x + (long long)it * stride];
-      mbar_wait(d_full + ts, (it >> 2) & 1);
+      um_wait(d_full + ts, (it >> 2) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (p.w_probe & 2) {  // development probe 2: no epilogue work
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty + ts);
+        continue;
+      }
       float acc[MT][4];
 #pragma unroll
       for (int m = 0; m < MT; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;

@@ -335,3 +335,82 @@ def test_non_power_of_two_dft_bluestein(speech, monkeypatch, cfg_name):
         assert np.abs(a - want).max() <= LOG_TOL
     else:
         check_linear(a.astype(np.float64), want)
+
+
+# ---- stft_umma_kernel: the transform on tcgen05 (opt-in, PDS_STFT_KERNEL=u) ----------------------
+UMMA_KERNEL = "pds::stft_umma_kernel"
+
+
+@pytest.mark.parametrize("name", sorted(cases.STFT_CASES))
+def test_tcgen05_kernel_matches_reference_golden(speech, golden, monkeypatch, name):
+    """Every reference golden through the tcgen05 transform (four 128-point real DFTs per frame as fp16
+    two-term GEMMs, radix-4 + filter bank in the epilogue warps); configurations the kernel does not
+    take (dft_size other than 512, operands beyond shared memory) must fall back and still be right"""
+    monkeypatch.setenv("PDS_STFT_KERNEL", "u")
+    cfg, _ = cases.STFT_CASES[name]
+    data = golden("stft")
+    signal = data[name + "/signal"]
+    want = data[name + "/feats"]
+    computer = build(speech, cfg)
+    got = computer.compute_full(signal)
+    eligible = computer._dft_size == 512 and computer.frame_shift % 4 == 0 and len(computer._truncated_filts) <= 64
+    if name in ("readme_fbank_wav", "readme_fbank_noise", "kaldi_fbank", "gammatone64"):
+        assert eligible and computer.kernel_name() == UMMA_KERNEL
+    print(f"{name}: {computer.kernel_name()}")
+    assert got.shape == want.shape
+    if cfg.get("use_log", True):
+        assert np.abs(got - want).max() <= LOG_TOL
+        lin = build(speech, dict(cfg, use_log=False))
+        check_linear(lin.compute_full(signal).astype(np.float64), data[name + "/feats_linear"], "tcgen05 " + name)
+    else:
+        check_linear(got.astype(np.float64), want, "tcgen05 " + name)
+
+
+@pytest.mark.parametrize("cfg_name", ["readme", "kaldi", "gammatone", "magnitude", "no_energy"])
+def test_tcgen05_kernel_ragged_batches_and_inputs(speech, monkeypatch, cfg_name):
+    """ragged batch (empty, shorter than a frame, partial tiles, several tiles) against the oracle and the
+    default kernel; 16-bit PCM input; fused pre-emphasis and dither (same Philox stream as the default
+    kernel, so the two agree to rounding)"""
+    cfg = {
+        "readme": cases.README_FBANK,
+        "kaldi": cases.KALDI_FBANK,
+        "gammatone": cases.GAMMATONE_64,
+        "magnitude": dict(cases.README_FBANK, use_power=False, use_log=False),
+        "no_energy": dict(cases.README_FBANK, include_energy=False),
+    }[cfg_name]
+    rng = np.random.default_rng(12)
+    lengths = [0, 1, 201, 399, 5000, 16000, 33333, 160 * 32 + 240, 160 * 64 + 241, 160 * 95, 48000] * 2
+    signals = [(rng.standard_normal(n) * 1000).astype(np.float32) for n in lengths]
+    # a quiet utterance next to loud ones, and one with an offset: the per-frame scale at work
+    signals.append((rng.standard_normal(20000) * 1e-3).astype(np.float32))
+    signals.append((rng.standard_normal(20000) * 1000 + 2000).astype(np.float32))
+    computer = build(speech, cfg)
+    monkeypatch.delenv("PDS_STFT_KERNEL", raising=False)
+    ref = computer.compute_batch(signals)
+    monkeypatch.setenv("PDS_STFT_KERNEL", "u")
+    got = computer.compute_batch(signals)
+    assert computer.kernel_name() == UMMA_KERNEL
+    for sig, a, b in zip(signals, got, ref):
+        want = oracle_feats(computer, sig.astype(np.float64))
+        assert a.shape == b.shape == want.shape
+        if not len(want):
+            continue
+        if computer._log:
+            assert np.abs(a - want).max() <= LOG_TOL
+        else:
+            check_linear(a.astype(np.float64), want)
+        assert np.array_equal(a, computer.compute_full(sig))  # batches and single signals: same bits
+    pcm = rng.integers(-20000, 20000, 30000).astype(np.int16)
+    a16 = computer.compute_batch([pcm])[0]
+    assert np.array_equal(a16, computer.compute_batch([pcm.astype(np.float32)])[0])
+    for kwargs in (dict(preemph=0.97), dict(dither=2.0, preemph=0.97, dither_first=True, seed=7),
+                   dict(dither=1.0, seed=3)):
+        monkeypatch.setenv("PDS_STFT_KERNEL", "u")
+        a = computer.compute_batch(signals[4:8] + [pcm], **kwargs)
+        monkeypatch.delenv("PDS_STFT_KERNEL")
+        b = computer.compute_batch(signals[4:8] + [pcm], **kwargs)
+        for x, y in zip(a, b):
+            if computer._log:
+                assert np.abs(x - y).max() <= 2e-4
+            else:
+                assert np.allclose(x, y, rtol=1e-4, atol=1e-4 * np.abs(y).max())

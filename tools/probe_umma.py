@@ -63,7 +63,10 @@ else:
     offsets, total = PackedSignals.layout(lens, 199 % 4)  # pad_left % 4: every tile starts on a 16-byte grid (TMA path)
     d_sig = torch.randn(total, device=dev) * 1000
     hours = lens.sum() / 16000 / 3600
-    for kernel in ((None, "u") if mode == "time" else ("u",)):
+    probe_ix = 0
+    for kernel in ((None, "u") if mode == "time" else ("u",) * (4 if mode == "probe" else 1)):
+        if mode == "probe":
+            os.environ["PDS_W_PROBE"] = str(probe_ix); probe_ix += 1
         if kernel:
             os.environ["PDS_STFT_KERNEL"] = kernel
         else:
