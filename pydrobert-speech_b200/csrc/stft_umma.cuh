@@ -94,9 +94,9 @@ __host__ __device__ inline UmLayout um_layout(int kch, int span_max, int L) {
 
 // wait of a warp that expects to wait: a few polls, then back off so that the spinning does not take
 // issue slots from the warps that do the work (bounded like mbar_wait)
-__device__ __forceinline__ void um_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void um_wait(uint64_t* bar, uint32_t parity, bool sleepy = true) {
   for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-    if (spins >= 2) __nanosleep(64);
+    if (spins >= 2 && sleepy) __nanosleep(64);
     if (spins > (1u << 22)) __trap();
   }
 }
@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
   int2* const s_steps = reinterpret_cast<int2*>(um_smem + lay.steps);  // {mask of filter tiles, first fragment}
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool sleepy = !(p.w_probe & 4);  // development probe 4: waits spin without backing off
   const int n_tiles = (int)p.n_tiles, stride = gridDim.x;
   const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + stride - 1) / stride : 0;
 
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
     }
     const bool ragged = (valid & 3) != 0;  // frame lengths that are not a multiple of four: per-sample mask
     const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(128 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
-    const uint32_t b_hi = smem_u32(um_smem + lay.b), b_lo = b_hi + lay.b_term;
+    const uint64_t db_hi = um_desc(smem_u32(um_smem + lay.b), kUmLboB), db_lo = um_desc(smem_u32(um_smem + lay.b) + lay.b_term, kUmLboB);
     const bool want_energy = p.include_energy != 0;
 
     // stage the samples of `tile` (use number `use` of sample stage xs): TMA bulk copy by one thread once every
@@ -235,13 +236,13 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
       float* s_xn = reinterpret_cast<float*>(um_smem + lay.x + xs * lay.x_stage);
       const bool by_hand = a1 - a0 < span;
       if (by_hand) {
-        um_wait(x_empty + xs, (use & 1) ^ 1);
+        um_wait(x_empty + xs, (use & 1) ^ 1, sleepy);
         stage_samples_slow<T, kUmBuildThreads>(s_xn, p, tile, span, a0, a1, btid);
         named_bar_sync(1, kUmBuildThreads);  // hand-staged samples are visible before x_full completes
       }
       if (btid == 0) {
         if (a1 > a0) {
-          if (!by_hand) um_wait(x_empty + xs, (use & 1) ^ 1);
+          if (!by_hand) um_wait(x_empty + xs, (use & 1) ^ 1, sleepy);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           mbar_expect_tx(x_full + xs, (a1 - a0) * 4);
           bulk_copy_g2s(s_xn + a0, sig + tile.sig_off + tile.start + a0, (a1 - a0) * 4, x_full + xs);
@@ -260,8 +261,8 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
       // the descriptor after the next one is fetched a whole tile ahead of its use
       const pds_tile after = it + 2 < my_tiles ? p.tiles[first + (long long)(it + 2) * stride] : next;
       if (it + 1 < my_tiles) stage_tile(next, (it + 1) & 1, (it + 1) >> 1);
-      um_wait(x_full + as, (it >> 1) & 1);
-      um_wait(a_empty + as, ((it >> 1) & 1) ^ 1);
+      um_wait(x_full + as, (it >> 1) & 1, sleepy);
+      um_wait(a_empty + as, ((it >> 1) & 1) ^ 1, sleepy);
       const float* __restrict__ s_x = reinterpret_cast<const float*>(um_smem + lay.x + as * lay.x_stage);
       uint8_t* const a_stage = um_smem + lay.a + as * lay.a_stage;
       const int ring = (it & (kUmRing - 1)) * kUmFrames;
@@ -342,18 +343,22 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
         if (lane == 0) {
           s_count[as] = 0;
           mbar_wait(a_full + as, (it >> 1) & 1);
-          um_wait(d_empty + ts, ((it >> 2) & 1) ^ 1);
+          um_wait(d_empty + ts, ((it >> 2) & 1) ^ 1, sleepy);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_hi = smem_u32(a_stage), a_lo = a_hi + lay.a_term;
+          // descriptors differ in their address field only: one 64-bit add per MMA, fully unrolled
+          const uint64_t da_hi = um_desc(smem_u32(a_stage), kUmLboA), da_lo = um_desc(smem_u32(a_stage) + lay.a_term, kUmLboA);
           const uint32_t d = tmem + 128 * ts;
-          for (int st = 0; st < kch / 2; ++st) {
-            const uint64_t ah = um_desc(a_hi + st * 2 * kUmLboA, kUmLboA), al = um_desc(a_lo + st * 2 * kUmLboA, kUmLboA);
-            const uint64_t bh = um_desc(b_hi + st * 2 * kUmLboB, kUmLboB), bl = um_desc(b_lo + st * 2 * kUmLboB, kUmLboB);
-            um_mma(d, ah, bh, idesc, st > 0);
-            um_mma(d, al, bh, idesc, 1);
-            um_mma(d, ah, bl, idesc, 1);
-            um_mma(d, al, bl, idesc, 1);  // 2^-22 of the product: free on the tensor pipe, and it keeps
-                                          // coefficients 60 dB below the frame's peak inside the tolerance
+#pragma unroll
+          for (int st = 0; st < kUmMaxKch / 2; ++st) {
+            if (st < kch / 2) {
+              const uint64_t ah = da_hi + (uint64_t)(st * ((2 * kUmLboA) >> 4)), al = da_lo + (uint64_t)(st * ((2 * kUmLboA) >> 4));
+              const uint64_t bh = db_hi + (uint64_t)(st * ((2 * kUmLboB) >> 4)), bl = db_lo + (uint64_t)(st * ((2 * kUmLboB) >> 4));
+              um_mma(d, ah, bh, idesc, st > 0);
+              um_mma(d, al, bh, idesc, 1);
+              um_mma(d, ah, bl, idesc, 1);
+              um_mma(d, al, bl, idesc, 1);  // 2^-22 of the product: free on the tensor pipe, and it keeps
+                                            // coefficients 60 dB below the frame's peak inside the tolerance
+            }
           }
           um_commit(a_empty + as);
           um_commit(d_full + ts);
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(kUmThreads, 1) stft_umma_kernel(const __grid_c
     for (int it = grp; it < my_tiles; it += 2) {
       const int ts = it & 3;
       const pds_tile tile = p.tiles[blockIdx.x + (long long)it * stride];
-      um_wait(d_full + ts, (it >> 2) & 1);
+      um_wait(d_full + ts, (it >> 2) & 1, sleepy);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (p.w_probe & 2) {  // development probe 2: no epilogue work
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
