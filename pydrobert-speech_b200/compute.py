@@ -725,7 +725,8 @@ class ShortIntegrationFrameComputer(LinearFilterBankFrameComputer):
 
         from ._lib import PdsSiDesc, check, get_lib
 
-        key = (device.index, os.environ.get("PDS_SI_KERNEL", ""), float(config.LOG_FLOOR_VALUE))
+        key = (device.index, os.environ.get("PDS_SI_KERNEL", ""), os.environ.get("PDS_SI_PAIRS", ""),
+               float(config.LOG_FLOOR_VALUE))
         plan = self._plans.get(key)
         if plan is not None:
             return plan

@@ -47,6 +47,9 @@ struct SiParams {
   const float2* hc_big;    // [C][R][1024] conj(DFT_N(h_c)) / N, element k = R * n1 + n2 at [n2][n1]
   const float2* tw_big;    // [R][1024]    W_N^(n2 * k1) at [n2][k1]
   int big_R;
+  // real banks: two filters share one complex transform, y1 - i y2 = FFT(conj(X) (Hc1 - i Hc2)); `hc` and
+  // `hc_big` then hold ceil(C / 2) combined spectra
+  int paired;
 };
 
 // y index i of the full convolution reads padded samples i-k; padded index q maps to x[q - pad_left].
@@ -248,7 +251,7 @@ __device__ __forceinline__ void si_fft1024(cplx (&z)[32], int lane, const float2
   Dft<32>::run(z);
 }
 
-template <bool POWER>
+template <bool POWER, bool PAIRED>
 __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_constant__ SiParams p) {
   extern __shared__ __align__(16) float smem[];
   const int S = p.S, M = p.M, C = p.C, V = p.valid_per_fft, TF = p.tile_frames;
@@ -298,9 +301,11 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
     // tasks (c, j) are dealt round-robin over the warps; each task writes the half-window sums
     // of the hops its block touches into slots of its own ([block][hop][half][c]), which the
     // final pass adds in a fixed order: bitwise reproducible without atomics
-    for (int task = warp; task < C * nfft; task += kSiFftWarps) {
-      const int c = task / nfft, j = task - c * nfft;
-      const float2* __restrict__ hc = p.hc + (size_t)c * kSiFftN + lane;
+    const int CT = PAIRED ? (C + 1) / 2 : C;  // transforms per block: filters, or pairs of real filters
+    for (int task = warp; task < CT * nfft; task += kSiFftWarps) {
+      const int ct = task / nfft, j = task - ct * nfft;
+      const int c = PAIRED ? 2 * ct : ct;
+      const float2* __restrict__ hc = p.hc + (size_t)ct * kSiFftN + lane;
       const cplx* __restrict__ X = s_X + j * kSiFftN + lane;
       cplx z[32];
 #pragma unroll
@@ -310,9 +315,14 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
       // sample j*V + n - (M-1) of the tile
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
-        float u = cnorm(z[r]);
-        if (!POWER) u = approx_sqrt(u);  // |y|: one MUFU, 2 ulp, branch free
-        s_u[lane + 32 * r] = u;
+        if (PAIRED) {  // z = y1 - i y2 with y1, y2 real: the second filter's row sits 1024 floats further
+          s_u[lane + 32 * r] = POWER ? cre(z[r]) * cre(z[r]) : fabsf(cre(z[r]));
+          s_u[kSiFftN + lane + 32 * r] = POWER ? cim(z[r]) * cim(z[r]) : fabsf(cim(z[r]));
+        } else {
+          float u = cnorm(z[r]);
+          if (!POWER) u = approx_sqrt(u);  // |y|: one MUFU, 2 ulp, branch free
+          s_u[lane + 32 * r] = u;
+        }
       }
       __syncwarp();
       const int lo_blk = j * V, hi_blk = min(lo_blk + V, ny);
@@ -321,20 +331,33 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_kernel(const __grid_c
       for (int h = lo_blk / S; h * S < hi_blk; ++h) {
         const int lo = max(h * S, lo_blk), hi = min(h * S + S, hi_blk);
         const float* __restrict__ w1 = s_w - h * S;  // first half-window, indexed by r
-        float a1 = 0.f, a2 = 0.f;
+        float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
         for (int r = lo + lane; r < hi; r += 32) {
-          const float u = ub[r];
-          a1 = fmaf(w1[r], u, a1);
-          a2 = fmaf(w1[S + r], u, a2);
+          const float u = ub[r], wa = w1[r], wb = w1[S + r];
+          a1 = fmaf(wa, u, a1);
+          a2 = fmaf(wb, u, a2);
+          if (PAIRED) {
+            const float v = ub[kSiFftN + r];
+            b1 = fmaf(wa, v, b1);
+            b2 = fmaf(wb, v, b2);
+          }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
           a1 += __shfl_xor_sync(0xffffffffu, a1, off);
           a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+          if (PAIRED) {
+            b1 += __shfl_xor_sync(0xffffffffu, b1, off);
+            b2 += __shfl_xor_sync(0xffffffffu, b2, off);
+          }
         }
         if (lane == 0) {
           part[(2 * h) * C] = a1;
           part[(2 * h + 1) * C] = a2;
+          if (PAIRED && c + 1 < C) {
+            part[(2 * h) * C + 1] = b1;
+            part[(2 * h + 1) * C + 1] = b2;
+          }
         }
       }
       __syncwarp();
@@ -403,7 +426,7 @@ __device__ __forceinline__ void si_fft1024_row(cplx (&z)[32], int lane, const fl
   Dft<32>::run(z);
 }
 
-template <bool POWER, int R>
+template <bool POWER, int R, bool PAIRED>
 __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_big_kernel(const __grid_constant__ SiParams p) {
   constexpr int N = kSiFftN * R, SLOTS = kSiFftWarps / R;
   extern __shared__ __align__(16) float smem[];
@@ -459,10 +482,11 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_big_kernel(const __gr
     }
     __syncthreads();
 
-    // ---- 16 / R filters at a time -----------------------------------------------------------
-    for (int c0 = 0; c0 < C; c0 += SLOTS) {
+    // ---- 16 / R transforms at a time: filters, or pairs of real filters (y1 - i y2) ------------
+    const int CT = PAIRED ? (C + 1) / 2 : C;
+    for (int c0 = 0; c0 < CT; c0 += SLOTS) {
       const int c = c0 + slot;
-      if (c < C) {
+      if (c < CT) {
         const float2* __restrict__ hc = p.hc_big + ((size_t)c * R + n2) * kSiFftN + lane;
         const cplx* __restrict__ lo = s_xh + n2 * kSiBigRowStride + lane;
         // k = R n1 + n2 > N / 2 is the conjugate of entry N - k: residue (R - n2) mod R, index
@@ -493,7 +517,7 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_big_kernel(const __gr
       // columns: |y|^p of output k1 + 1024 k2 of slot s replaces the real part of Z[s][k2][k1]
       for (int q = tid; q < SLOTS * kSiFftN; q += kSiFftThreads) {
         const int s = q / kSiFftN, col = q - s * kSiFftN;
-        if (c0 + s < C) {
+        if (c0 + s < CT) {
           cplx* __restrict__ zc = s_z + s * N + col;
           cplx v[R];
 #pragma unroll
@@ -501,9 +525,14 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_big_kernel(const __gr
           Dft<R>::run(v);
 #pragma unroll
           for (int k = 0; k < R; ++k) {
-            float u = cnorm(v[k]);
-            if (!POWER) u = approx_sqrt(u);
-            reinterpret_cast<float*>(zc + k * kSiFftN)[0] = u;
+            if (PAIRED) {  // both real filters: |y1|^p replaces the real part, |y2|^p the imaginary part
+              zc[k * kSiFftN] = cmake(POWER ? cre(v[k]) * cre(v[k]) : fabsf(cre(v[k])),
+                                      POWER ? cim(v[k]) * cim(v[k]) : fabsf(cim(v[k])));
+            } else {
+              float u = cnorm(v[k]);
+              if (!POWER) u = approx_sqrt(u);
+              reinterpret_cast<float*>(zc + k * kSiFftN)[0] = u;
+            }
           }
         }
       }
@@ -511,15 +540,23 @@ __global__ void __launch_bounds__(kSiFftThreads, 1) si_fft_big_kernel(const __gr
       // pooling: frame t of slot s = window . |y|^p[(M - 1) + t S ... + 2 S)
       for (int task = warp; task < SLOTS * nframes; task += kSiFftWarps) {
         const int s = task / nframes, t = task - s * nframes;
-        if (c0 + s >= C) continue;
+        if (c0 + s >= CT) continue;
         const float* __restrict__ u = s_zf + 2 * (s * N + (M - 1) + t * S);
-        float acc = 0.f;
-        for (int n = lane; n < 2 * S; n += 32) acc = fmaf(s_w[n], u[2 * n], acc);
+        float acc = 0.f, acc2 = 0.f;
+        for (int n = lane; n < 2 * S; n += 32) {
+          acc = fmaf(s_w[n], u[2 * n], acc);
+          if (PAIRED) acc2 = fmaf(s_w[n], u[2 * n + 1], acc2);
+        }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        for (int off = 16; off > 0; off >>= 1) {
+          acc += __shfl_xor_sync(0xffffffffu, acc, off);
+          if (PAIRED) acc2 += __shfl_xor_sync(0xffffffffu, acc2, off);
+        }
         if (lane == 0) {
-          if (p.use_log) acc = __logf(fmaxf(acc, p.log_floor));
-          p.out[(tile.out_row + t) * C + c0 + s] = acc;
+          if (p.use_log) acc = __logf(fmaxf(acc, p.log_floor)), acc2 = __logf(fmaxf(acc2, p.log_floor));
+          const int cf = PAIRED ? 2 * (c0 + s) : c0 + s;
+          p.out[(tile.out_row + t) * C + cf] = acc;
+          if (PAIRED && cf + 1 < C) p.out[(tile.out_row + t) * C + cf + 1] = acc2;
         }
       }
       __syncthreads();
@@ -542,6 +579,7 @@ struct pds_si_plan {
   size_t fft_smem_bytes = 0;
   int fft_grid_limit = 0;
   int big_R = 0;  // > 0: si_fft_big_kernel with blocks of 1024 * big_R points
+  bool paired = false;  // real bank on an overlap-save kernel: two filters per complex transform
   size_t big_smem_bytes = 0;
   SiParams params{};
   void* d_blob = nullptr;
@@ -571,17 +609,26 @@ void host_fft(std::vector<std::complex<double>>& a) {
 }
 
 using SiKernel = void (*)(const SiParams);
-const void* pick_si_big(const pds_si_plan* plan) {
-  switch (plan->big_R * 2 + (plan->power ? 1 : 0)) {
-    case 4: return reinterpret_cast<const void*>(si_fft_big_kernel<false, 2>);
-    case 5: return reinterpret_cast<const void*>(si_fft_big_kernel<true, 2>);
-    case 8: return reinterpret_cast<const void*>(si_fft_big_kernel<false, 4>);
-    case 9: return reinterpret_cast<const void*>(si_fft_big_kernel<true, 4>);
-    case 16: return reinterpret_cast<const void*>(si_fft_big_kernel<false, 8>);
-    case 17: return reinterpret_cast<const void*>(si_fft_big_kernel<true, 8>);
-    case 32: return reinterpret_cast<const void*>(si_fft_big_kernel<false, 16>);
-    default: return reinterpret_cast<const void*>(si_fft_big_kernel<true, 16>);
+template <bool PAIRED>
+const void* pick_si_big_p(int big_R, bool power) {
+  switch (big_R * 2 + (power ? 1 : 0)) {
+    case 4: return reinterpret_cast<const void*>(si_fft_big_kernel<false, 2, PAIRED>);
+    case 5: return reinterpret_cast<const void*>(si_fft_big_kernel<true, 2, PAIRED>);
+    case 8: return reinterpret_cast<const void*>(si_fft_big_kernel<false, 4, PAIRED>);
+    case 9: return reinterpret_cast<const void*>(si_fft_big_kernel<true, 4, PAIRED>);
+    case 16: return reinterpret_cast<const void*>(si_fft_big_kernel<false, 8, PAIRED>);
+    case 17: return reinterpret_cast<const void*>(si_fft_big_kernel<true, 8, PAIRED>);
+    case 32: return reinterpret_cast<const void*>(si_fft_big_kernel<false, 16, PAIRED>);
+    default: return reinterpret_cast<const void*>(si_fft_big_kernel<true, 16, PAIRED>);
   }
+}
+const void* pick_si_big(const pds_si_plan* plan) {
+  return plan->paired ? pick_si_big_p<true>(plan->big_R, plan->power) : pick_si_big_p<false>(plan->big_R, plan->power);
+}
+const void* pick_si_fft(const pds_si_plan* plan) {
+  if (plan->paired)
+    return plan->power ? reinterpret_cast<const void*>(si_fft_kernel<true, true>) : reinterpret_cast<const void*>(si_fft_kernel<false, true>);
+  return plan->power ? reinterpret_cast<const void*>(si_fft_kernel<true, false>) : reinterpret_cast<const void*>(si_fft_kernel<false, false>);
 }
 SiKernel pick_si(const pds_si_plan* plan) {
   if (plan->real) return plan->power ? si_direct_kernel<true, true> : si_direct_kernel<true, false>;
@@ -630,6 +677,12 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
     }
     if (plan->big_R) plan->fft = false;
   }
+  // real banks on the overlap-save kernels: filters 2 p and 2 p + 1 share one complex transform
+  // (PDS_SI_PAIRS=0 keeps one transform per filter: A/B runs, tests)
+  {
+    const char* pairs = getenv("PDS_SI_PAIRS");
+    plan->paired = plan->real && (plan->fft || plan->big_R) && !(pairs && pairs[0] == '0');
+  }
   const int big_N = kSiFftN * plan->big_R;
   const size_t o_hc = (o_w + 2 * (size_t)plan->S * sizeof(float) + 15) & ~(size_t)15;
   const size_t o_tw = o_hc + (plan->fft ? (size_t)plan->C * kSiFftN * sizeof(float2) : 0);
@@ -641,13 +694,24 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
     const int R = plan->big_R;
     const double two_pi = 6.283185307179586476925286766559;
     float2* hcb = reinterpret_cast<float2*>(blob.data() + o_hcb);
-    std::vector<std::complex<double>> h(big_N);
+    std::vector<std::complex<double>> h(big_N), acc_pair(big_N);
     for (int c = 0; c < plan->C; ++c) {
       std::fill(h.begin(), h.end(), std::complex<double>(0.0, 0.0));
       for (int m = 0; m < plan->M; ++m)
         h[m] = std::complex<double>(d->h_real[(size_t)c * plan->M + m],
                                     plan->real ? 0.0 : d->h_imag[(size_t)c * plan->M + m]);
       host_fft(h);
+      if (plan->paired) {
+        // Hc1 - i Hc2 with Hc = conj(H) / N = (a, b): (a1 + b2, b1 - a2); pair p at index p
+        for (int k = 0; k < big_N; ++k) {
+          const double a = h[k].real() / big_N, b = -h[k].imag() / big_N;
+          acc_pair[k] = (c % 2 == 0) ? std::complex<double>(a, b) : acc_pair[k] + std::complex<double>(b, -a);
+        }
+        if (c % 2 == 1 || c == plan->C - 1)
+          for (int k = 0; k < big_N; ++k)
+            hcb[((size_t)(c / 2) * R + k % R) * kSiFftN + k / R] = make_float2((float)acc_pair[k].real(), (float)acc_pair[k].imag());
+        continue;
+      }
       for (int k = 0; k < big_N; ++k)  // conj(H[k]) / N at [k mod R][k div R]
         hcb[((size_t)c * R + k % R) * kSiFftN + k / R] =
             make_float2((float)(h[k].real() / big_N), (float)(-h[k].imag() / big_N));
@@ -670,6 +734,7 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
     std::vector<double> cs(kSiFftN), sn(kSiFftN);
     for (int i = 0; i < kSiFftN; ++i) cs[i] = std::cos(two_pi * i / kSiFftN), sn[i] = std::sin(two_pi * i / kSiFftN);
     float2* hc = reinterpret_cast<float2*>(blob.data() + o_hc);
+    std::vector<std::complex<double>> pair_acc(kSiFftN);
     for (int c = 0; c < plan->C; ++c)
       for (int k = 0; k < kSiFftN; ++k) {
         double re = 0.0, im = 0.0;  // H[k] = sum_m h[m] e^{-2 pi i k m / N}
@@ -680,8 +745,16 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
           re += hr * cs[a] + hi * sn[a];
           im += hi * cs[a] - hr * sn[a];
         }
-        // conj(H) / N at [reg = k / 32][lane = k % 32]
-        hc[(size_t)c * kSiFftN + (k / 32) * 32 + (k % 32)] = make_float2((float)(re / kSiFftN), (float)(-im / kSiFftN));
+        // conj(H) / N at [reg = k / 32][lane = k % 32]; real banks: (a1 + b2, b1 - a2) of filters 2 p, 2 p + 1 at p
+        const double a = re / kSiFftN, b = -im / kSiFftN;
+        if (!plan->paired) {
+          hc[(size_t)c * kSiFftN + k] = make_float2((float)a, (float)b);
+        } else if (c % 2 == 0) {
+          pair_acc[k] = std::complex<double>(a, b);
+          if (c == plan->C - 1) hc[(size_t)(c / 2) * kSiFftN + k] = make_float2((float)a, (float)b);
+        } else {
+          hc[(size_t)(c / 2) * kSiFftN + k] = make_float2((float)(pair_acc[k].real() + b), (float)(pair_acc[k].imag() - a));
+        }
       }
     float2* tw = reinterpret_cast<float2*>(blob.data() + o_tw);
     for (int k1 = 0; k1 < 32; ++k1)
@@ -716,6 +789,7 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
   p.hc_big = reinterpret_cast<const float2*>(base + o_hcb);
   p.tw_big = reinterpret_cast<const float2*>(base + o_twb);
   p.big_R = plan->big_R;
+  p.paired = plan->paired ? 1 : 0;
   if (plan->big_R) {
     p.valid_per_fft = big_N - (plan->M - 1);
     p.tile_frames = p.valid_per_fft / plan->S - 1;
@@ -769,8 +843,7 @@ extern "C" int pds_si_plan_create(const pds_si_desc* d, int device, pds_si_plan*
     plan->fft = p.ffts_per_tile <= kSiFftWarps && plan->fft_smem_bytes <= prop.sharedMemPerBlockOptin;
   }
   if (plan->fft) {
-    const void* fn = plan->power ? reinterpret_cast<const void*>(si_fft_kernel<true>)
-                                 : reinterpret_cast<const void*>(si_fft_kernel<false>);
+    const void* fn = pick_si_fft(plan);
     err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->fft_smem_bytes);
     if (err != cudaSuccess) {
       cudaGetLastError();
@@ -854,10 +927,9 @@ extern "C" int pds_si_run(pds_si_plan* plan, const float* d_signal, const pds_ti
   }
   if (plan->fft) {
     const int grid = (int)std::min<int64_t>(n_tiles, plan->fft_grid_limit);
-    if (plan->power)
-      si_fft_kernel<true><<<grid, kSiFftThreads, plan->fft_smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
-    else
-      si_fft_kernel<false><<<grid, kSiFftThreads, plan->fft_smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+    void* args[] = {&p};
+    PDS_CUDA_CHECK(cudaLaunchKernel(pick_si_fft(plan), dim3(grid), dim3(kSiFftThreads), args, plan->fft_smem_bytes,
+                                    static_cast<cudaStream_t>(stream)));
     PDS_CUDA_CHECK(cudaGetLastError());
     return PDS_OK;
   }

@@ -302,3 +302,30 @@ def test_si_long_kernel_on_short_supports(speech, golden, monkeypatch, name):
     got = computer.compute_full(signal)
     assert got.shape == want.shape
     assert np.abs(got - want).max() <= (1e-3 if cfg.get("use_log", True) else 1e-4 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("bank", ["fbank", {"name": "fbank", "num_filts": 7}, {"name": "fbank", "num_filts": 8},
+                                  {"name": "fbank", "num_filts": 3}, {"name": "fbank", "num_filts": 2}])
+def test_si_real_banks_share_transforms(speech, monkeypatch, bank):
+    """real banks: filters 2 p and 2 p + 1 ride one complex transform (y1 - i y2) on both overlap-save
+    kernels; against one transform per filter (PDS_SI_PAIRS=0) and against the oracle, odd and even
+    numbers of filters"""
+    rng = np.random.default_rng(31)
+    signal = (rng.standard_normal(9000) * 1000).astype(np.float32)
+    for cfg in ({"name": "si", "bank": bank}, {"name": "si", "bank": bank, "use_power": True, "use_log": False},
+                {"name": "si", "bank": bank, "frame_shift_ms": 20}):
+        monkeypatch.setenv("PDS_SI_PAIRS", "0")
+        single = build(speech, speech.compute.FrameComputer, cfg).compute_full(signal)
+        monkeypatch.delenv("PDS_SI_PAIRS")
+        computer = build(speech, speech.compute.FrameComputer, cfg)
+        paired = computer.compute_full(signal)
+        want = oracle.si_features(
+            signal.astype(np.float64), computer._impulse_responses, computer._window.reshape(-1), computer.frame_shift,
+            computer._zero_pad, computer._pool_start, computer._frames_lost, cfg.get("use_power", False),
+            cfg.get("use_log", True))
+        assert paired.shape == single.shape == want.shape
+        if cfg.get("use_log", True):
+            assert np.abs(paired - want).max() <= 1e-3 and np.abs(paired - single).max() <= 2e-4
+        else:
+            scale = np.maximum(np.abs(want), 1e-6 * np.abs(want).max(axis=1, keepdims=True))
+            assert (np.abs(paired - want) / scale).max() <= 1e-4

@@ -13,6 +13,7 @@ from pydrobert_speech_b200.compute import PackedSignals  # noqa: E402
 dev = torch.device("cuda", 0)
 banks = {
     "fbank40 (6 987 taps)": "fbank",
+    "fbank3 (wide filters)": {"name": "fbank", "num_filts": 3},
     "gabor128 (838 taps)": {"name": "gabor", "scaling_function": "mel", "num_filts": 128},
     "gammatone100 (934 taps)": {"name": "gammatone", "scaling_function": "mel", "num_filts": 100},
 }
@@ -22,11 +23,13 @@ offsets, total = PackedSignals.layout(lengths, 0)
 d_sig = torch.randn(total, device=dev) * 1000
 hours = lengths.sum() / 16000 / 3600
 for label, bank in banks.items():
-    for kernel in ("", "direct"):
-        if kernel:
+    for kernel in ("", "unpaired", "direct"):
+        os.environ.pop("PDS_SI_KERNEL", None)
+        os.environ.pop("PDS_SI_PAIRS", None)
+        if kernel == "unpaired":
+            os.environ["PDS_SI_PAIRS"] = "0"
+        elif kernel:
             os.environ["PDS_SI_KERNEL"] = kernel
-        else:
-            os.environ.pop("PDS_SI_KERNEL", None)
         try:
             si = pds.alias_factory_subclass_from_arg(pds.compute.FrameComputer, {"name": "si", "bank": bank})
             out = si.compute_packed_device(d_sig, offsets, lengths)
