@@ -9,8 +9,11 @@ stand in for the reference's inside ``signals-to-torch-feat-dir``).
 
 Differences worth knowing:
 
-* the modules are inference-only -- the window and filters are buffers, not parameters, and no
-  gradient flows through the kernels;
+* the forward pass of the STFT module is the fused CUDA kernel; its window and filters are learnable
+  parameters like the reference's (``torch.py:362-366``) and gradients with respect to them and to the
+  signal are produced in the backward pass by a plain-torch restatement of the same arithmetic
+  (:func:`_stft_math`), so training code written against the reference runs unchanged.  The other
+  modules (pre-processing, short integration, post-processors) are inference only;
 * complex banks follow the *NumPy* path of the reference, which is what ``BASELINE.json`` names as
   the oracle; the reference's own torch path disagrees with its NumPy path there
   (``torch.py:213-214`` vs ``compute.py:436-438``, see SURVEY.md section 4);
@@ -25,6 +28,7 @@ import numpy as np
 import torch
 
 from . import config
+from ._tables import _segment_bins, half_spectrum_len, stft_geometry
 from .compute import SIFrameComputer, STFTFrameComputer
 from .post import PostProcessor
 from .pre import Dither, Preemphasize
@@ -134,6 +138,101 @@ class PyTorchDither(torch.nn.Module):
         return pytorch_dither(sig, self.coeff)
 
 
+def _stft_math(
+    sig: torch.Tensor,
+    filters: Sequence[torch.Tensor],
+    offsets: Sequence[int],
+    frame_length: int,
+    frame_shift: int,
+    centered: bool,
+    window: Optional[torch.Tensor],
+    dft_size: int,
+    use_log: bool,
+    use_power: bool,
+    include_energy: bool,
+    kaldi_shift: bool,
+    is_real: bool,
+    eps: float,
+) -> torch.Tensor:
+    """What the fused kernel computes, restated in differentiable torch ops (BACKWARD pass only)
+
+    Same quantities as ``compute.py:388-460`` / ``torch.py:142-235`` of the reference, arranged the
+    way the kernel arranges them: symmetric padding, strided frames, ``|rfft|^p`` once, then one
+    matrix product with the folded weights ``W[f, bin] = sum_taps |h_f[tap]|^p`` (the tap -> bin map
+    replays the reference's segment walk, :func:`_tables._segment_bins`), doubled for real banks.
+    Nothing on the forward path calls this.
+    """
+    n = sig.size(0)
+    num_frames, pad_left, pad_right = stft_geometry(n, frame_length, frame_shift, centered, kaldi_shift)
+    if pad_left or pad_right:
+        sig = torch.cat([sig[:pad_left].flip(0), sig, sig[n - pad_right:].flip(0)])
+    frames = sig.unfold(0, frame_length, frame_shift)[:num_frames]
+    columns = []
+    if include_energy:
+        energy = frames.square().mean(1)
+        columns.append((energy if use_power else energy.sqrt()).unsqueeze(1))
+    if window is not None:
+        frames = frames * window.to(frames.dtype)
+    spect = torch.fft.rfft(frames, dft_size, dim=1)
+    spect = spect.real.square() + spect.imag.square() if use_power else spect.abs()
+    half_len = half_spectrum_len(dft_size) if dft_size % 2 == 0 else (dft_size + 1) // 2
+    rows = []
+    for offset, filt in zip(offsets, filters):
+        gain = filt.abs().to(spect.dtype)
+        if use_power:
+            gain = gain.square()
+        pieces = _segment_bins(int(offset), int(filt.numel()), half_len)
+        bins = torch.as_tensor(np.concatenate(pieces or [np.arange(0)]).astype(np.int64), device=gain.device)
+        rows.append(torch.zeros(half_len, dtype=spect.dtype, device=gain.device).index_add(0, bins, gain))
+    weights = torch.stack(rows)
+    if is_real:
+        weights = weights * 2
+    columns.append(spect @ weights.t())
+    feats = torch.cat(columns, 1)
+    return feats.clamp_min(eps).log() if use_log else feats
+
+
+class _STFTFunction(torch.autograd.Function):
+    """Forward: the fused CUDA kernel.  Backward: autograd through :func:`_stft_math`"""
+
+    @staticmethod
+    def forward(ctx, module, signal, window, *filters):
+        ctx.module = module
+        ctx.has_window = window is not None
+        ctx.save_for_backward(signal, *([window] if window is not None else []), *filters)
+        return module._kernel_forward(signal)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from ._gpu import current_device
+
+        module = ctx.module
+        saved = ctx.saved_tensors
+        signal, rest = saved[0], list(saved[1:])
+        window = rest.pop(0) if ctx.has_window else None
+        filters = rest
+        device = signal.device if signal.device.type == "cuda" else current_device()
+        needs = ctx.needs_input_grad  # (module, signal, window, *filters)
+        work = signal.dtype if signal.dtype in (torch.float32, torch.float64) else torch.float32
+        with torch.enable_grad():
+            sig = signal.detach().to(device=device, dtype=work).requires_grad_(needs[1])
+            win = None if window is None else window.detach().to(device).requires_grad_(needs[2])
+            filts = [f.detach().to(device).requires_grad_(needs[3 + i]) for i, f in enumerate(filters)]
+            out = _stft_math(
+                sig, filts, module.offsets, module.frame_length, module.frame_shift, module.centered, win,
+                module.dft_size, module.use_log, module.use_power, module.include_energy, module.kaldi_shift,
+                module.is_real, float(config.LOG_FLOOR_VALUE))
+            wanted = [t for t in [sig, win] + filts if t is not None and t.requires_grad]
+            grads = list(torch.autograd.grad(out, wanted, grad_out.to(device=device, dtype=out.dtype))) if wanted else []
+        result = [None]
+        for original, leaf in zip([signal, window] + list(filters), [sig, win] + filts):
+            if leaf is None or not leaf.requires_grad:
+                result.append(None)
+            else:
+                result.append(grads.pop(0).to(device=original.device, dtype=original.dtype))
+        return tuple(result)
+
+
 class PyTorchShortTimeFourierTransformFrameComputer(torch.nn.Module):
     """Fused-kernel STFT features as a module (reference ``torch.py:238-429``)
 
@@ -185,20 +284,23 @@ class PyTorchShortTimeFourierTransformFrameComputer(torch.nn.Module):
         self.kaldi_shift, self.is_real, self.include_energy = kaldi_shift, is_real, include_energy
         self._frame_style = frame_style
         # Same parameter names as the reference (torch.py:362-366: ``filters.<i>`` and ``window``), so
-        # its state_dicts load here and ours load there.  They do not require gradients: the kernels
-        # are inference only (see forward()).
-        self.filters = torch.nn.ParameterList(
-            [torch.nn.Parameter(torch.as_tensor(f).clone(), requires_grad=False) for f in filters])
+        # its state_dicts load here and ours load there; learnable, like the reference's.
+        self.filters = torch.nn.ParameterList([torch.nn.Parameter(torch.as_tensor(f).clone()) for f in filters])
         if window is None:
             self.register_parameter("window", None)
         else:
-            self.window = torch.nn.Parameter(window.detach().clone(), requires_grad=False)
+            self.window = torch.nn.Parameter(window.detach().clone())
         self._computer = None
         self._rebuild()
         self.register_load_state_dict_post_hook(lambda module, _: module._rebuild())
 
+    def _versions(self):
+        return tuple(p._version for p in self.parameters())
+
     def _rebuild(self) -> None:
-        """(Re)build the kernel plan from the current parameters (construction, load_state_dict)"""
+        """(Re)build the kernel plan from the current parameters (construction, load_state_dict, and
+        whenever an optimizer step or any other in-place update has touched them)"""
+        self._built_versions = self._versions()
         window = None if self.window is None else self.window.detach().cpu().double().numpy()
         self._computer = STFTFrameComputer.from_tables(
             list(self.offsets), [f.detach().cpu().numpy() for f in self.filters], self.frame_length,
@@ -227,23 +329,28 @@ class PyTorchShortTimeFourierTransformFrameComputer(torch.nn.Module):
         self.kaldi_shift, self.is_real = computer._kaldi_shift, computer._real
         self.include_energy = computer._include_energy
         self._frame_style = computer.frame_style
-        self.filters = torch.nn.ParameterList([torch.nn.Parameter(x, requires_grad=False) for _, x in pairs])
-        self.window = torch.nn.Parameter(torch.as_tensor(computer._window).to(window_type), requires_grad=False)
+        self.filters = torch.nn.ParameterList([torch.nn.Parameter(x) for _, x in pairs])
+        self.window = torch.nn.Parameter(torch.as_tensor(computer._window).to(window_type))
         self._computer = computer  # full-precision tables: no float32/complex64 round trip
+        self._built_versions = self._versions()
         self.register_load_state_dict_post_hook(lambda module, _: module._rebuild())
         return self
 
     def forward(self, signal: torch.Tensor) -> torch.Tensor:
-        computer = self._computer
         if signal.ndim != 1:
             raise RuntimeError(f"Expected x to be 1-dimensional; got {signal.ndim}")
-        if signal.requires_grad and torch.is_grad_enabled():
-            raise RuntimeError(
-                "the B200 kernels are inference only: no gradient flows through "
-                "PyTorchSTFTFrameComputer; detach() the signal or run under torch.no_grad()")
         if signal.size(0) < self.frame_length // 2 + 1:
             # like the reference (torch.py:179-180): num_filts columns, without the energy column
             return signal.new_empty((0, len(self.offsets)))
+        if self._versions() != self._built_versions:
+            self._rebuild()  # the parameters were updated in place (optimizer step): new kernel tables
+        if torch.is_grad_enabled() and (signal.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return _STFTFunction.apply(self, signal, self.window, *self.filters)
+        return self._kernel_forward(signal)
+
+    def _kernel_forward(self, signal: torch.Tensor) -> torch.Tensor:
+        computer = self._computer
+        signal = signal.detach()
         d_sig, home = _on_device(signal)
         if d_sig.dtype not in (torch.float32, torch.int16):
             d_sig = d_sig.float()

@@ -5,7 +5,8 @@ Run in the build container (the reference is importable there, not on the GPU bo
     python tests/golden/make_golden.py
 
 Outputs (committed): ``stft.npz``, ``si.npz``, ``banks.npz``, ``post.npz``, ``kaldi.npz``, ``extra.npz``,
-``si_long.npz`` (``python tests/golden/make_golden.py extra`` / ``si_long`` rebuild the last two alone).
+``si_long.npz``, ``torch_grad.npz`` (``python tests/golden/make_golden.py extra`` / ``si_long`` / ``torch_grad``
+rebuild the last three alone).
 The reference's numpy path is used (``config.USE_FFTPACK = False``); its scipy.fftpack branch
 is pinned to it by the reference's own tests.  Nothing here is imported at test time except
 ``cases.py``.
@@ -211,7 +212,49 @@ def si_long_goldens():
     np.savez_compressed(os.path.join(HERE, "si_long.npz"), **out)
 
 
+TORCH_GRAD_CASES = {  # real banks only: the reference's torch path and its NumPy path agree there
+    "fbank10_power_log_energy": dict(bank={"name": "fbank", "num_filts": 10}, frame_length_ms=25, include_energy=True,
+                                     window_function="hanning", use_power=True, use_log=True),
+    "fbank8_magnitude_causal": dict(bank={"name": "fbank", "num_filts": 8}, frame_length_ms=20, frame_shift_ms=8,
+                                    frame_style="causal", include_energy=False, window_function="hamming",
+                                    use_power=False, use_log=False),
+}
+
+
+def torch_grad_goldens():
+    """``torch_grad.npz``: outputs and gradients (signal, window, every filter) of the reference's OWN torch
+    module (``torch.py:142-235``) in float64, for the backward pass of the torch mirror"""
+    import torch
+    from pydrobert.speech import torch as ref_torch
+
+    out = {}
+    rng = np.random.default_rng(77)
+    for name, kwargs in TORCH_GRAD_CASES.items():
+        computer = build(compute.FrameComputer, dict(kwargs, name="stft"))
+        module = ref_torch.PyTorchSTFTFrameComputer.from_stft_frame_computer(computer, torch.cdouble, torch.double)
+        signal = torch.tensor(rng.standard_normal(3000) * 100.0, dtype=torch.double, requires_grad=True)
+        feats = module(signal)
+        grad_out = torch.tensor(rng.standard_normal(tuple(feats.shape)))
+        leaves = [signal, module.window] + list(module.filters)
+        grads = torch.autograd.grad(feats, leaves, grad_out)
+        out[name + "/signal"] = signal.detach().numpy()
+        out[name + "/feats"] = feats.detach().numpy()
+        out[name + "/grad_out"] = grad_out.numpy()
+        out[name + "/grad_signal"] = grads[0].numpy()
+        out[name + "/window"] = module.window.detach().numpy()
+        out[name + "/grad_window"] = grads[1].numpy()
+        out[name + "/offsets"] = np.array(computer._filt_start_idxs, dtype=np.int64)
+        ragged(name + "/filters", [f.detach().numpy() for f in module.filters], out)
+        ragged(name + "/grad_filters", [g.numpy() for g in grads[2:]], out)
+        out[name + "/geometry"] = np.array(
+            [computer.frame_length, computer.frame_shift, computer._dft_size, int(computer.frame_style == "centered")])
+    np.savez_compressed(os.path.join(HERE, "torch_grad.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "torch_grad":
+        torch_grad_goldens()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "extra":
         extra_goldens()
         sys.exit(0)
@@ -225,6 +268,7 @@ if __name__ == "__main__":
     kaldi_goldens()
     extra_goldens()
     si_long_goldens()
+    torch_grad_goldens()
     for name in sorted(os.listdir(HERE)):
         if name.endswith(".npz"):
             print(name, os.path.getsize(os.path.join(HERE, name)))

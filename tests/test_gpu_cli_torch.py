@@ -31,21 +31,21 @@ def test_pytorch_stft_frame_computer(speech, include_energy):
     exp = computer.compute_full(signal.numpy())
     act = module(signal)
     assert act.device.type == "cpu" and act.dtype == torch.float32
-    assert np.allclose(exp, act.numpy(), atol=1e-5)
+    assert np.allclose(exp, act.detach().numpy(), atol=1e-5)
     on_gpu = module(signal.cuda().double())
     assert on_gpu.is_cuda and on_gpu.dtype == torch.float64
-    assert np.allclose(exp, on_gpu.cpu().numpy(), atol=1e-5)
+    assert np.allclose(exp, on_gpu.detach().cpu().numpy(), atol=1e-5)
     # built from explicit tables (float32 / complex64 like the reference's from_* default)
     rebuilt = PyTorchSTFTFrameComputer(
         list(zip(module.offsets, module.filters)), module.frame_length, module.frame_shift, "centered",
         module.window, module.dft_size, module.use_log, module.use_power, module.include_energy,
         module.kaldi_shift, module.is_real)
-    assert np.allclose(exp, rebuilt(signal).numpy(), atol=1e-4)
+    assert np.allclose(exp, rebuilt(signal).detach().numpy(), atol=1e-4)
     func = pytorch_stft_frame_computer(
         signal, module.filters, list(module.offsets), module.frame_length, module.frame_shift, True,
         module.window, module.dft_size, module.use_log, module.use_power, module.include_energy,
         module.kaldi_shift, module.is_real)
-    assert np.allclose(exp, func.numpy(), atol=1e-4)
+    assert np.allclose(exp, func.detach().numpy(), atol=1e-4)
     assert module(torch.zeros(10)).shape == (0, len(module.offsets))  # as the reference, torch.py:179-180
     with pytest.raises(RuntimeError, match="1-dimensional"):
         module(torch.zeros(3, 100))
@@ -279,7 +279,7 @@ def test_torch_module_state_dict_is_the_references(speech):
     state = module.state_dict()
     assert sorted(state) == sorted([f"filters.{i}" for i in range(40)] + ["window"])
     assert state["window"].shape == (400,) and state["filters.0"].dtype == torch.cfloat
-    assert all(not p.requires_grad for p in module.parameters())
+    assert all(p.requires_grad for p in module.parameters())  # learnable, like the reference's
     sig = torch.randn(6000)
     before = module(sig)
     halved = {k: (v * 0.5 if k.startswith("filters") else v) for k, v in state.items()}
@@ -290,8 +290,7 @@ def test_torch_module_state_dict_is_the_references(speech):
     energy = pt.PyTorchSTFTFrameComputer.from_stft_frame_computer(build(speech, cases.README_FBANK))
     assert energy(torch.zeros(10)).shape == (0, 40)
     assert energy(torch.zeros(5000)).shape[1] == 41
-    with pytest.raises(RuntimeError, match="inference only"):
-        module(torch.randn(3000, requires_grad=True))
+    assert module(torch.randn(3000, requires_grad=True)).grad_fn is not None  # differentiable (next test)
     with torch.no_grad():
         assert module(torch.randn(3000, requires_grad=True)).shape[1] == 40
 
@@ -343,3 +342,67 @@ def test_compute_feats_from_kaldi_tables(speech, tmp_path):
     # unreadable table / bad computer config: return code 1, no exception
     assert command_line.compute_feats_from_kaldi_tables(["scp:" + str(tmp_path / "nope"), "ark:" + feat_ark, cfg]) == 1
     assert command_line.compute_feats_from_kaldi_tables(["scp:" + wav_scp, "ark:" + feat_ark, '{"name": "nonsense"}']) == 1
+
+
+def _grad_case(golden, name):
+    import torch
+
+    data = golden("torch_grad")
+    edges = data[name + "/filters/offsets"]
+    filters = [torch.tensor(data[name + "/filters/values"][a:b]) for a, b in zip(edges[:-1], edges[1:])]
+    grad_filters = [data[name + "/grad_filters/values"][a:b] for a, b in zip(edges[:-1], edges[1:])]
+    frame_length, frame_shift, dft_size, centered = (int(v) for v in data[name + "/geometry"])
+    kwargs = dict(frame_length=frame_length, frame_shift=frame_shift, dft_size=dft_size,
+                  frame_style="centered" if centered else "causal",
+                  use_log=name.endswith("energy"), use_power=name.endswith("energy"),
+                  include_energy=name.endswith("energy"), kaldi_shift=False, is_real=True)
+    return data, filters, grad_filters, [int(o) for o in data[name + "/offsets"]], kwargs
+
+
+@pytest.mark.parametrize("name", ["fbank10_power_log_energy", "fbank8_magnitude_causal"])
+def test_torch_module_is_differentiable(speech, golden, name):
+    """forward = the fused kernel, backward = autograd through the plain-torch restatement: outputs and the
+    gradients with respect to the signal, the window and every filter against the reference's OWN torch
+    module (float64, tests/golden/make_golden.py torch_grad); an in-place parameter update (what an optimizer
+    step does) reaches the next forward"""
+    import torch
+
+    import pydrobert_speech_b200.torch as pt
+
+    data, filters, grad_filters, offsets, kwargs = _grad_case(golden, name)
+    module = pt.PyTorchSTFTFrameComputer(
+        list(zip(offsets, filters)), kwargs["frame_length"], kwargs["frame_shift"], kwargs["frame_style"],
+        torch.tensor(data[name + "/window"]), kwargs["dft_size"], kwargs["use_log"], kwargs["use_power"],
+        kwargs["include_energy"], kwargs["kaldi_shift"], kwargs["is_real"])
+    signal = torch.tensor(data[name + "/signal"], dtype=torch.float32, device="cuda", requires_grad=True)
+    feats = module(signal)
+    want = data[name + "/feats"]
+    assert feats.is_cuda and feats.grad_fn is not None and tuple(feats.shape) == want.shape
+    got = feats.detach().cpu().numpy()
+    if kwargs["use_log"]:
+        assert np.abs(got - want).max() <= 1e-3
+    else:
+        assert (np.abs(got - want) / np.maximum(np.abs(want), 1e-6 * np.abs(want).max())).max() <= 1e-4
+    feats.backward(torch.tensor(data[name + "/grad_out"], dtype=torch.float32, device="cuda"))
+
+    def close(a, b):
+        a = a.detach().cpu().numpy()
+        return np.abs(a - b).max() <= 2e-4 * np.abs(b).max()
+
+    assert close(signal.grad, data[name + "/grad_signal"])
+    assert close(module.window.grad, data[name + "/grad_window"])
+    for p, g in zip(module.filters, grad_filters):
+        assert close(p.grad, g)
+    # one step of plain SGD on the window, then the forward pass must see the new window
+    before = module(signal.detach())
+    with torch.no_grad():
+        module.window.mul_(0.5)
+    after = module(signal.detach())
+    shift = float(np.log(4.0)) if kwargs["use_log"] else None
+    cols = slice(1, None) if kwargs["include_energy"] else slice(None)
+    if shift is not None:
+        assert torch.allclose(after[:, cols], before[:, cols] - shift, atol=2e-3)
+    else:
+        assert torch.allclose(after[:, cols], before[:, cols] * 0.5, rtol=1e-3, atol=1e-3 * float(before.detach().abs().max()))
+    with torch.no_grad():
+        assert module(signal).grad_fn is None

@@ -150,3 +150,28 @@ def test_si_oracle_long_supports(speech, golden, name):
     want = data[name + "/feats"]
     assert got.shape == want.shape
     assert np.allclose(got, want, rtol=2e-6, atol=2e-6)  # the golden is stored as float32
+
+
+@pytest.mark.parametrize("name", ["fbank10_power_log_energy", "fbank8_magnitude_causal"])
+def test_torch_restatement_gradients_match_the_reference(speech, golden, name):
+    """``torch._stft_math`` (the backward pass of the torch mirror) in float64 on the CPU: outputs and
+    gradients of the reference's own torch module (tests/golden/make_golden.py torch_grad)"""
+    import torch
+
+    import pydrobert_speech_b200.torch as pt
+
+    data = golden("torch_grad")
+    edges = data[name + "/filters/offsets"]
+    filters = [torch.tensor(data[name + "/filters/values"][a:b], requires_grad=True) for a, b in zip(edges[:-1], edges[1:])]
+    frame_length, frame_shift, dft_size, centered = (int(v) for v in data[name + "/geometry"])
+    full = name.endswith("energy")
+    signal = torch.tensor(data[name + "/signal"], requires_grad=True)
+    window = torch.tensor(data[name + "/window"], requires_grad=True)
+    feats = pt._stft_math(signal, filters, [int(o) for o in data[name + "/offsets"]], frame_length, frame_shift,
+                          bool(centered), window, dft_size, full, full, full, False, True, 1e-5)
+    assert np.allclose(feats.detach().numpy(), data[name + "/feats"], rtol=1e-10, atol=1e-10)
+    grads = torch.autograd.grad(feats, [signal, window] + filters, torch.tensor(data[name + "/grad_out"]))
+    assert np.allclose(grads[0].numpy(), data[name + "/grad_signal"], rtol=1e-8, atol=1e-12)
+    assert np.allclose(grads[1].numpy(), data[name + "/grad_window"], rtol=1e-8, atol=1e-9)
+    for g, (a, b) in zip(grads[2:], zip(edges[:-1], edges[1:])):
+        assert np.allclose(g.numpy(), data[name + "/grad_filters/values"][a:b], rtol=1e-8, atol=1e-9)
