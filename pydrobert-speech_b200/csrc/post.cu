@@ -380,34 +380,14 @@ __global__ void __launch_bounds__(kDeltaThreads, 4) deltas25s_kernel(const __gri
           for (int j = 8; j < 16; ++j) w[j] = src[(long long)j * cols];
         }
         carried = interior;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (q >= n) break;
-          float d0, d1 = 0.f, d2 = 0.f;
-          if (interior) {
-            d0 = w[q + 4];
-#pragma unroll
-            for (int j = 0; j < 5; ++j) d1 = fmaf(f1[j], w[q + 2 + j], d1);
-#pragma unroll
-            for (int j = 0; j < 9; ++j) d2 = fmaf(f2[j], w[q + j], d2);
-          } else {
-            const long long rr = r + q;
-            if (rr > hi) {
-              while (p.row_off[u + 1] <= rr) ++u;
-              lo = p.row_off[u], hi = p.row_off[u + 1] - 1;
-            }
-            d0 = in[rr * cols];
-#pragma unroll
-            for (int j = 0; j < 5; ++j) d1 = fmaf(f1[j], in[max(lo, min(hi, rr + j - 2)) * cols], d1);
-#pragma unroll
-            for (int j = 0; j < 9; ++j) d2 = fmaf(f2[j], in[max(lo, min(hi, rr + j - 4)) * cols], d2);
-          }
+        // one row's three values: into the statistics, or out (normalised or not)
+        auto emit = [&](long long row, float d0, float d1, float d2) {
           if (MODE == kD25Stats) {
             sum[0] += (double)d0, sq[0] += (double)d0 * d0;
             sum[1] += (double)d1, sq[1] += (double)d1 * d1;
             sum[2] += (double)d2, sq[2] += (double)d2 * d2;
           } else {
-            float* __restrict__ dst = p.out + (r + q) * out_cols + c;
+            float* __restrict__ dst = p.out + row * out_cols + c;
             if (MODE == kD25Apply) {
               __stcs(dst, fmaf(d0, scale[0], -shift[0]));
               __stcs(dst + cols, fmaf(d1, scale[1], -shift[1]));
@@ -417,6 +397,31 @@ __global__ void __launch_bounds__(kDeltaThreads, 4) deltas25s_kernel(const __gri
               __stcs(dst + cols, d1);
               __stcs(dst + 2 * cols, d2);
             }
+          }
+        };
+        if (interior) {  // eight rows straight from the window: no per-row branches
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) d1 = fmaf(f1[j], w[q + 2 + j], d1);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) d2 = fmaf(f2[j], w[q + j], d2);
+            emit(r + q, w[q + 4], d1, d2);
+          }
+        } else {  // within four rows of an utterance boundary, or the tail of the run: clamped loads
+          for (int q = 0; q < n; ++q) {
+            const long long rr = r + q;
+            if (rr > hi) {
+              while (p.row_off[u + 1] <= rr) ++u;
+              lo = p.row_off[u], hi = p.row_off[u + 1] - 1;
+            }
+            float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) d1 = fmaf(f1[j], in[max(lo, min(hi, rr + j - 2)) * cols], d1);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) d2 = fmaf(f2[j], in[max(lo, min(hi, rr + j - 4)) * cols], d2);
+            emit(rr, in[rr * cols], d1, d2);
           }
         }
       }

@@ -1,4 +1,5 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_cli_torch.py -x -q > gpurun_out/pytest_torch.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/pytest_torch.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:deltas25s -s 4 -c 2 -o gpurun_out/prof_post -f python tools/probe_post.py > gpurun_out/ncu_post2.log 2>&1
+echo "ncu rc=$?"; tail -3 gpurun_out/ncu_post2.log
