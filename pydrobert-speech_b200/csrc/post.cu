@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kDeltaThreads) deltas25_kernel(const __grid_co
 constexpr int kD25sRunStats = 128, kD25sRunStore = 16;
 
 template <int MODE>
-__global__ void __launch_bounds__(kDeltaThreads, 4) deltas25s_kernel(const __grid_constant__ DeltaParams p) {
+__global__ void __launch_bounds__(kDeltaThreads, MODE == kD25Stats ? 4 : 3) deltas25s_kernel(const __grid_constant__ DeltaParams p) {
   __shared__ long long s_utt[2];
   extern __shared__ __align__(16) float s_dyn[];  // statistics fold (MODE 1)
   const int tid = threadIdx.x, cols = p.cols, out_cols = 3 * cols;
@@ -359,7 +359,8 @@ __global__ void __launch_bounds__(kDeltaThreads, 4) deltas25s_kernel(const __gri
       long long u = s_utt[parity];
       long long lo = 0, hi = -1;  // rows of the current utterance (inclusive)
       float w[16];                // w[j] = x[r + j - 4] for the group's first row r
-      bool carried = false;
+      float nxt[8];               // rows r + 12 .. r + 19, requested while this group computes
+      bool carried = false, have_nxt = false;
       for (long long r = r_begin; r < r_end; r += 8) {
         if (r > hi) {  // (re)locate the utterance of row r
           while (p.row_off[u + 1] <= r) ++u;
@@ -376,8 +377,20 @@ __global__ void __launch_bounds__(kDeltaThreads, 4) deltas25s_kernel(const __gri
 #pragma unroll
             for (int j = 0; j < 8; ++j) w[j] = src[(long long)j * cols];
           }
+          if (carried && have_nxt) {
 #pragma unroll
-          for (int j = 8; j < 16; ++j) w[j] = src[(long long)j * cols];
+            for (int j = 0; j < 8; ++j) w[8 + j] = nxt[j];
+          } else {
+#pragma unroll
+            for (int j = 8; j < 16; ++j) w[j] = src[(long long)j * cols];
+          }
+          // software pipeline (storing passes: three CTAs per SM at 80 registers; the statistics pass is issue
+          // bound and keeps four): the next group's new rows are requested before this group's arithmetic
+          have_nxt = MODE != kD25Stats && r + 4 >= lo && r + 19 <= hi && r_end - (r + 8) >= 8;
+          if (have_nxt) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nxt[j] = src[(long long)(16 + j) * cols];
+          }
         }
         carried = interior;
         // one row's three values: into the statistics, or out (normalised or not)
@@ -696,7 +709,7 @@ int run_deltas(int mode, const float* d_in, float* d_out, int64_t total_rows, in
       static const int run_env = getenv("PDS_D25_RUN") ? std::max(8, atoi(getenv("PDS_D25_RUN")) / 8 * 8) : 0;
       static const int grid_env = getenv("PDS_D25_GRID") ? std::max(1, atoi(getenv("PDS_D25_GRID"))) : 0;
       const int run_rows = run_env ? run_env : (mode == kD25Stats ? kD25sRunStats : kD25sRunStore);
-      const int ctas_per_sm = grid_env ? grid_env : (mode == kD25Stats ? 16 : 8);
+      const int ctas_per_sm = grid_env ? grid_env : (mode == kD25Stats ? 16 : 12);  // whole waves of 4 / 3 resident CTAs
       p.rows_per_cta = run_rows;
       const long long chunk_rows = (long long)(kDeltaThreads / n_cols) * run_rows;
       const long long n_chunks = (total_rows + chunk_rows - 1) / chunk_rows;
