@@ -709,7 +709,7 @@ int run_deltas(int mode, const float* d_in, float* d_out, int64_t total_rows, in
       static const int run_env = getenv("PDS_D25_RUN") ? std::max(8, atoi(getenv("PDS_D25_RUN")) / 8 * 8) : 0;
       static const int grid_env = getenv("PDS_D25_GRID") ? std::max(1, atoi(getenv("PDS_D25_GRID"))) : 0;
       const int run_rows = run_env ? run_env : (mode == kD25Stats ? kD25sRunStats : kD25sRunStore);
-      const int ctas_per_sm = grid_env ? grid_env : (mode == kD25Stats ? 16 : 12);  // whole waves of 4 / 3 resident CTAs
+      const int ctas_per_sm = grid_env ? grid_env : 24;  // whole waves of the 4 (statistics) or 3 (storing passes) resident CTAs
       p.rows_per_cta = run_rows;
       const long long chunk_rows = (long long)(kDeltaThreads / n_cols) * run_rows;
       const long long n_chunks = (total_rows + chunk_rows - 1) / chunk_rows;
