@@ -175,3 +175,24 @@ def test_torch_restatement_gradients_match_the_reference(speech, golden, name):
     assert np.allclose(grads[1].numpy(), data[name + "/grad_window"], rtol=1e-8, atol=1e-9)
     for g, (a, b) in zip(grads[2:], zip(edges[:-1], edges[1:])):
         assert np.allclose(g.numpy(), data[name + "/grad_filters/values"][a:b], rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", sorted(cases.STFT_CASES))
+def test_torch_restatement_matches_every_stft_golden(speech, golden, name):
+    """the differentiable restatement behind the torch mirror's backward pass computes what the kernels
+    compute: every STFT golden of the reference's NumPy path (complex banks included), float64 on the CPU"""
+    import torch
+
+    import pydrobert_speech_b200.torch as pt
+
+    cfg, _ = cases.STFT_CASES[name]
+    data = golden("stft")
+    computer = speech.alias_factory_subclass_from_arg(speech.compute.FrameComputer, cfg)
+    filters = [torch.as_tensor(np.asarray(f)) for f in computer._truncated_filts]
+    feats = pt._stft_math(
+        torch.tensor(data[name + "/signal"].astype(np.float64)), filters, computer._filt_start_idxs, computer.frame_length,
+        computer.frame_shift, computer.frame_style == "centered", torch.as_tensor(computer._window), computer._dft_size,
+        computer._log, computer._power, computer._include_energy, computer._kaldi_shift, computer._real, 1e-5)
+    want = data[name + "/feats"]
+    assert tuple(feats.shape) == want.shape
+    assert np.allclose(feats.numpy(), want, rtol=1e-9, atol=1e-9)
