@@ -1,5 +1,6 @@
 #!/bin/bash
+# scratch session script (development): edit, then `gpurun -- 'bash tools/gpu/scratch.sh'`
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:deltas25s -s 10 -c 1 -o gpurun_out/prof_post_apply -f python tools/probe_post.py > gpurun_out/ncu_post3.log 2>&1
-echo "ncu rc=$?"; tail -3 gpurun_out/ncu_post3.log
+timeout 300 python tools/probe_post.py 2>&1 | tail -1
+timeout 300 python tools/probe_umma.py time 2>&1 | tail -2
